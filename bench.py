@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- RDC time-steps/s of the rdcFEs hot path (FE assembly + Krylov solve) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n CELLS]
+
+Workload (BASELINE.json metric, SURVEY.md 8d case S1): ADPM operators (parameter set P-full: every term
+active) on the synthetic unit-cube Kuhn-tet mesh n=119 -> 10 110 954 tets, 1 728 000 nodes, 5.18 M dofs,
+dt = 0.05.  One "step" = one pass of the time-loop body adpm.C:63-76: rotate time levels, assemble K and F,
+GMRES(30)+Jacobi solve to rtol 1e-12, check_solution.
+  * value : device-resident steps/s (inputs in HBM when the timed region starts), CUDA events, max over ranks
+  * e2e   : the same step through the C ABI with HOST buffers every step: rdc_set_solution (pinned H2D) ->
+            rdc_step -> rdc_get_solution (D2H)
+  * roofline : the dominant kernel (block-CSR SpMV): algorithmic bytes / mean launch time, timed live with an
+            event pair around every SpMV launch of the timed steps; assembly reported next to it
+  * cpu_baseline : the CPU oracle (port of the reference path: element loop + scalar CSR + GMRES(30) +
+            block-Jacobi/ILU(0)) on the box's host cores, on a bounded sample mesh, scaled per element
+N > 1 (torchrun): strong scaling of the same mesh, METIS node partition, NCCL halo exchange + all-reduce.
+--impl reference: times the CPU port only (the real rdcFEs binary needs libMesh/PETSc/MPI: not installable).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+DT = 0.05
+METRIC = "rdc_time_steps_per_s_10Mtet_adpm"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload(n):
+    from rdcfes_b200 import synth
+    conn, xyz = synth.kuhn_cube(n)
+    u0, tracts = synth.adpm_fields(conn, xyz, smooth=True)
+    return conn, xyz, synth.adpm_params("full"), u0, tracts
+
+
+def cpu_port_run(n, steps, warmup, nthreads):
+    """The CPU port on a bounded sample mesh: returns (seconds per step, elements, its per step, phases)."""
+    from oracle import oracle as O
+    conn, xyz, params, u0, tracts = workload(n)
+    pr = O.Problem(O.ADPM, O.TET4, conn, xyz, params, u0, elem_field=tracts, nthreads=nthreads)
+    times, its_all, ta, ts = [], [], [], []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        its, _ = pr.step(DT, pc=O.PC_ILU, nblocks=nthreads, restart=30, rtol=1e-12, maxits=5000)
+        t1 = time.perf_counter()
+        if k >= warmup:
+            times.append(t1 - t0); its_all.append(its); ta.append(pr.t_assemble); ts.append(pr.t_solve)
+    return float(np.mean(times)), conn.shape[0], float(np.mean(its_all)), float(np.mean(ta)), float(np.mean(ts))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (our libMesh-free port, oracle/) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = os.cpu_count() or 1
+    n_sample = args.cpu_n
+    sec, E, its, ta, ts = cpu_port_run(n_sample, args.steps, args.warmup, ncores)
+    E_full = 6 * args.n ** 3
+    value = 1.0 / (sec * E_full / E)
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"S1 ADPM P-full, unit-cube Kuhn tets n={args.n} ({E_full} tets), dt={DT}"},
+           "cpu_baseline": {"value": value, "unit": "steps/s", "cores": ncores, "kind": "port",
+                            "sample": f"n={n_sample} ({E} tets) timed {sec:.3f} s/step ({ta:.3f} assemble + {ts:.3f} solve, "
+                                      f"{its:.0f} GMRES(30)+BJacobi/ILU0 its), scaled x{E_full / E:.1f} by element count"},
+           "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--n", type=int, default=119, help="cells per edge (119 -> 10.1 M tets)")
+    ap.add_argument("--cpu-n", type=int, default=40, help="sample mesh of the CPU baseline")
+    ap.add_argument("--ksp", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partitioner", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from rdcfes_b200 import system as rs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(rs.make_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    t_setup0 = time.perf_counter()
+    conn, xyz, params, u0, tracts = workload(args.n)
+    N, E = xyz.shape[0], conn.shape[0]
+    sysm = rs.TransientRdcSystem(rs.ADPM, rs.TET4, conn, xyz, device=local, rank=rank, nranks=world,
+                                 partitioner=args.partitioner, unique_id=uid)
+    sysm.set_parameters(params)
+    sysm.set_elem_field(tracts)
+    sysm.ksp = args.ksp
+    stream = torch.cuda.current_stream()
+    sysm.set_stream(stream.cuda_stream)  # torch.cuda.Event on this stream brackets the library's kernels
+    u_host = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    u_np = u_host.numpy()
+    u_np[:] = u0.ravel()
+    sysm.set_solution(u_np)
+    t_setup = time.perf_counter() - t_setup0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident steps ("value")
+    for _ in range(args.warmup):
+        sysm.step(DT)
+    acc = {"its": 0, "ms_asm": 0.0, "ms_solve": 0.0, "ms_clamp": 0.0, "ms_spmv": 0.0, "n_spmv": 0}
+    launches0 = sysm.stats().kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        its, _ = sysm.step(DT)
+        st = sysm.stats()
+        acc["its"] += its; acc["ms_asm"] += st.ms_assemble; acc["ms_solve"] += st.ms_solve
+        acc["ms_clamp"] += st.ms_clamp; acc["ms_spmv"] += st.ms_spmv_total; acc["n_spmv"] += st.n_spmv
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sysm.stats().kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    steps_per_s = args.steps / (ms * 1e-3)
+
+    # ---------------------------------------------------------------- end to end through host buffers
+    e2e_steps = max(3, min(args.steps, 5))
+    barrier()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        sysm.set_solution(u_np)          # H2D of the step's input (pinned)
+        sysm.step(DT)
+        sysm.get_solution(u_np)          # D2H of the step's result
+    e1.record(stream)
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = e2e_steps / (ms_e2e * 1e-3)
+
+    st = sysm.stats()
+    if rank != 0:
+        sysm.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    spmv_ms = acc["ms_spmv"] / max(acc["n_spmv"], 1)
+    spmv_gbs = st.bytes_spmv / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
+    asm_ms = acc["ms_asm"] / args.steps
+    asm_gbs = st.bytes_assemble / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"S1 ADPM P-full, unit-cube Kuhn tets n={args.n} ({E} tets, {N} nodes, {3 * N} dofs), "
+                               f"dt={DT}, GMRES(30)+Jacobi rtol 1e-12" if args.ksp == 0 else
+                               f"S1 ADPM P-full n={args.n} ({E} tets), ksp={args.ksp}+Jacobi rtol 1e-12",
+                   "parallelism": f"node partition x{world} (METIS), NCCL halo + allreduce" if world > 1 else "single GPU",
+                   "l2": "operator (1.9 GB) and vectors far exceed the 126 MB L2; no flush needed between steps",
+                   "setup_s": round(t_setup, 2)},
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": 8 * 3 * N, "d2h_bytes_per_step": 8 * 3 * N,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_spmv<3> (block-CSR SpMV, fused Jacobi scaling)", "bound": "hbm",
+                     "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": None,
+                     "peak_source": peak_src, "bytes_per_launch": int(st.bytes_spmv), "ms_per_launch": spmv_ms,
+                     "launches_timed": acc["n_spmv"], "frac_of_nominal_8TBs": spmv_gbs / 8000.0},
+        "roofline_assembly": {"kernel": "k_assemble<Adpm,4,256>", "bound": "hbm", "achieved": asm_gbs, "peak": peak,
+                              "unit": "GB/s", "frac": asm_gbs / peak, "bytes_per_launch": int(st.bytes_assemble),
+                              "index_bytes_per_launch": int(st.bytes_index), "ms_per_launch": asm_ms},
+        "phases_ms_per_step": {"assemble": asm_ms, "solve": acc["ms_solve"] / args.steps,
+                               "clamp": acc["ms_clamp"] / args.steps, "spmv_in_solve": acc["ms_spmv"] / args.steps},
+        "krylov_its_per_step": acc["its"] / args.steps,
+    }
+    sysm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if not args.no_cpu_baseline:
+        ncores = os.cpu_count() or 1
+        sec, Es, its, ta, ts = cpu_port_run(args.cpu_n, 2, 1, ncores)
+        val = 1.0 / (sec * E / Es)
+        out["cpu_baseline"] = {"value": val, "unit": "steps/s", "cores": ncores, "kind": "port",
+                               "sample": f"n={args.cpu_n} ({Es} tets) {sec:.3f} s/step ({ta:.3f} assemble + {ts:.3f} solve, "
+                                         f"{its:.0f} GMRES(30)+BJacobi/ILU0 its), scaled x{E / Es:.1f} by element count"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -185,6 +185,7 @@ int rdc_get_solution(rdc_ctx*, double* u);      /* distributed: every rank recei
 int rdc_get_old_solution(rdc_ctx*, double* u);
 int64_t rdc_n_dofs(const rdc_ctx*);
 int rdc_set_time(rdc_ctx*, double time);        /* system.time (adpm.C:64) */
+int rdc_set_dt(rdc_ctx*, double dt);            /* es.parameters "time_step"; needed before RIPF's pre-loop rdc_clamp (ripf.C:53,697) */
 
 /* ---- the hot path ----------------------------------------------------------------------------- */
 int rdc_rotate(rdc_ctx*);                                   /* older <- old <- current */

@@ -1,0 +1,482 @@
+// assemble.cu -- deterministic, atomic-free FE assembly of K and F into the row-local block-CSR operator.
+//
+// Replaces the element loop of assemble_adpm / _pihna / _ripf / _proteas_model / _hcc
+// (adpm.C:416-650 and siblings): dof_indices, DenseMatrix Ke/Fe, fe->reinit, the qp x i x j nest and
+// add_matrix/add_vector (MatSetValues ADD_VALUES) are fused into one kernel.
+//
+// Work decomposition:
+//   * one thread per (owned node, incident element) PAIR -- the row of Ke that belongs to that node.
+//     Pairs are sorted by node, then element id; a CTA owns a run of whole nodes with <= PAIRS pairs.
+//   * phase 1: each thread gathers its element (connectivity, padded coordinates, old solution, element
+//     and nodal aux fields), evaluates geometry + the model's coefficient table at the quadrature points
+//     and forms ITS ROW of Ke (nen blocks of v x v) and of Fe in registers; rows go to shared memory.
+//   * phase 2: one thread per block of the CTA's rows sums the staged contributions in the fixed order of
+//     a precomputed contributor list (ascending element id == the reference's serial loop order) and
+//     writes every value of K exactly once, coalesced.  No float atomics; bit-reproducible.
+// Operator layout ("row-local SoA"): block row i has L_i blocks; entry (a,b) of block k of row i lives at
+//   val[rowptr[i]*v*v + (a*v+b)*L_i + k]   so that a half-warp reading one row is fully coalesced.
+#include <stdio.h>
+
+#include "models.cuh"
+#include "rdc_internal.h"
+
+namespace rdc {
+
+__constant__ FeTable c_fe[2];  // [0] TET4, [1] HEX8
+
+int upload_fe_tables() {
+  FeTable t[2];
+  fe_table_fill(&t[0], RDC_TET4);
+  fe_table_fill(&t[1], RDC_HEX8);
+  return cudaMemcpyToSymbol(c_fe, t, sizeof(t)) == cudaSuccess ? 0 : -1;
+}
+
+struct AsmArgs {
+  const int32_t* conn;
+  const double* xyz4;
+  const double* u_old;
+  const double* efield;
+  const double* aux0;   // RIPF: TD [n_loc*3]; PROTEAS: AUX [n_loc*2]
+  const double* aux1;   // RIPF: RT [n_loc*3]
+  const int32_t* n2e_ptr;
+  const int32_t* pair;
+  const int32_t* rowptr;
+  const int32_t* cta_node;
+  const int32_t* cptr;
+  const uint16_t* clist;
+  double* val;
+  double* rhs;
+};
+
+__host__ __device__ constexpr int popc(unsigned m) { int c = 0; while (m) { c += m & 1u; m >>= 1; } return c; }
+__host__ __device__ constexpr int slot_of(unsigned mask, int bitpos) { return popc(mask & ((1u << bitpos) - 1u)); }
+
+// value at a quadrature point, summed exactly like the reference does (adpm.C:464-471): mul then add
+template <int NEN>
+__device__ __forceinline__ double interp(const double* phi_q, const double* nodal) {
+  double v = 0.0;
+#pragma unroll
+  for (int l = 0; l < NEN; l++) v = v + phi_q[l] * nodal[l];
+  return v;
+}
+
+template <class M>
+__device__ __forceinline__ void load_aux(const AsmArgs& A, int node, double* out);
+template <> __device__ __forceinline__ void load_aux<Adpm>(const AsmArgs&, int, double*) {}
+template <> __device__ __forceinline__ void load_aux<Pihna>(const AsmArgs&, int, double*) {}
+template <> __device__ __forceinline__ void load_aux<Hcc>(const AsmArgs&, int, double*) {}
+template <> __device__ __forceinline__ void load_aux<Ripf>(const AsmArgs& A, int node, double* out) {
+  out[0] = A.aux0[(size_t)node * 3 + 1];  // TD(cc), ripf.C:470
+  out[1] = A.aux0[(size_t)node * 3 + 2];  // TD(fb), ripf.C:471
+  out[2] = A.aux1[(size_t)node * 3 + 2];  // RT_total, ripf.C:477
+}
+template <> __device__ __forceinline__ void load_aux<Proteas>(const AsmArgs& A, int node, double* out) {
+  out[0] = A.aux0[(size_t)node * 2 + 0];  // AUX variable 0 (proteas.C:472,481)
+}
+
+template <class M, int NEN, int PAIRS>
+__global__ void __launch_bounds__(PAIRS) k_assemble(const AsmArgs A, const typename M::Params P) {
+  constexpr int NV = M::NV;
+  constexpr int VV = NV * NV;
+  constexpr unsigned KMASK = M::CMASK | M::SMASK | M::TMASK;
+  constexpr int NKV = popc(KMASK);
+  constexpr int NQP = NEN == 4 ? 5 : 8;
+  constexpr int TI = NEN == 4 ? 0 : 1;
+  constexpr int NAUX = M::N_NAUX;
+  constexpr int NA_ = NAUX > 0 ? NAUX : 1;
+
+  extern __shared__ double smem[];
+  double* stageK = smem;                              // [NEN][NKV][PAIRS]
+  double* stageF = smem + (size_t)NEN * NKV * PAIRS;  // [NV][PAIRS]
+  __shared__ int s_rowptr[PAIRS + 1];
+
+  const int tid = threadIdx.x;
+  const int node0 = A.cta_node[blockIdx.x], node1 = A.cta_node[blockIdx.x + 1];
+  const int pair0 = A.n2e_ptr[node0], npairs = A.n2e_ptr[node1] - pair0;
+  const int nnode = node1 - node0;
+  for (int r = tid; r <= nnode; r += PAIRS) s_rowptr[r] = A.rowptr[node0 + r];
+
+  // ------------------------------------------------------------------ phase 1: one pair per thread
+  if (tid < npairs) {
+    const int pk = A.pair[pair0 + tid];
+    const int e = pk >> 3, li = pk & 7;
+    int en[NEN];
+    if constexpr (NEN == 4) {
+      const int4 c4 = reinterpret_cast<const int4*>(A.conn)[e];
+      en[0] = c4.x; en[1] = c4.y; en[2] = c4.z; en[3] = c4.w;
+    } else {
+      const int4 c4 = reinterpret_cast<const int4*>(A.conn)[2 * (size_t)e];
+      const int4 d4 = reinterpret_cast<const int4*>(A.conn)[2 * (size_t)e + 1];
+      en[0] = c4.x; en[1] = c4.y; en[2] = c4.z; en[3] = c4.w;
+      en[4] = d4.x; en[5] = d4.y; en[6] = d4.z; en[7] = d4.w;
+    }
+    double X[NEN][3], U[NV][NEN], AX[NA_][NEN];
+#pragma unroll
+    for (int l = 0; l < NEN; l++) {
+      const double2 xy = reinterpret_cast<const double2*>(A.xyz4)[2 * (size_t)en[l]];
+      const double z = A.xyz4[4 * (size_t)en[l] + 2];
+      X[l][0] = xy.x; X[l][1] = xy.y; X[l][2] = z;
+#pragma unroll
+      for (int a = 0; a < NV; a++) U[a][l] = A.u_old[(size_t)en[l] * NV + a];
+      if (NAUX > 0) {
+        double t[NA_];
+        load_aux<M>(A, en[l], t);
+#pragma unroll
+        for (int m = 0; m < NAUX; m++) AX[m][l] = t[m];
+      }
+    }
+    double ef[3] = {0.0, 0.0, 0.0};
+    if (M::N_EFIELD == 3) { ef[0] = A.efield[(size_t)e * 3]; ef[1] = A.efield[(size_t)e * 3 + 1]; ef[2] = A.efield[(size_t)e * 3 + 2]; }
+
+    double Kacc[NEN][NKV > 0 ? NKV : 1];
+    double Facc[NV];
+#pragma unroll
+    for (int j = 0; j < NEN; j++)
+#pragma unroll
+      for (int s = 0; s < NKV; s++) Kacc[j][s] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NV; a++) Facc[a] = 0.0;
+
+    const FeTable& T = c_fe[TI];
+
+    // per-qp body shared by both element types.  dphi[l][3] are the physical gradients at this qp.
+    auto qp_body = [&](int q, double JxW, const double (*dphi)[3], const double (*dir)[3], bool dirs_given) {
+      double phi_q[NEN];
+#pragma unroll
+      for (int l = 0; l < NEN; l++) phi_q[l] = T.phi[l][q];
+      double Uq[NV], Aq[NA_];
+#pragma unroll
+      for (int a = 0; a < NV; a++) Uq[a] = interp<NEN>(phi_q, U[a]);
+      Aq[0] = 0.0;
+      if (NAUX > 0) {
+        if (M::NV == 5 && NAUX == 1) {  // PROTEAS: RTD = phi_1(qp) * AUX0(local node 1), proteas.C:481
+          Aq[0] = 0.0 + phi_q[1] * AX[0][1];
+        } else {
+#pragma unroll
+          for (int m = 0; m < NAUX; m++) Aq[m] = interp<NEN>(phi_q, AX[m]);
+        }
+      }
+      double dirq[M::NDIR][3];
+      if (!dirs_given) {
+        double G[NV][3], GA[NA_][3];
+#pragma unroll
+        for (int a = 0; a < NV; a++)
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            double g = 0.0;
+            if (M::GRADMASK >> a & 1u) {
+#pragma unroll
+              for (int l = 0; l < NEN; l++) g = g + dphi[l][d] * U[a][l];
+            }
+            G[a][d] = g;
+          }
+#pragma unroll
+        for (int m = 0; m < NA_; m++)
+#pragma unroll
+          for (int d = 0; d < 3; d++) {
+            double g = 0.0;
+            if (NAUX > 0 && (M::AUXGRADMASK >> m & 1u)) {
+#pragma unroll
+              for (int l = 0; l < NEN; l++) g = g + dphi[l][d] * AX[m][l];
+            }
+            GA[m][d] = g;
+          }
+        M::directions(P, G, ef, GA, dirq);
+      }
+      // grad phi_i of MY row and phi_i, selected without dynamic register indexing
+      double dNi[3] = {dphi[0][0], dphi[0][1], dphi[0][2]};
+      double phi_i = phi_q[0];
+#pragma unroll
+      for (int l = 1; l < NEN; l++)
+        if (li == l) { dNi[0] = dphi[l][0]; dNi[1] = dphi[l][1]; dNi[2] = dphi[l][2]; phi_i = phi_q[l]; }
+      double Dg[M::NDIR];
+#pragma unroll
+      for (int m = 0; m < M::NDIR; m++) Dg[m] = dirs_given ? dot3(dir[m], dNi) : dot3(dirq[m], dNi);
+      Coef<NV> k;
+      M::coef(P, Uq, Aq, Dg, k);
+      const double Wi = JxW * phi_i;
+#pragma unroll
+      for (int a = 0; a < NV; a++) Facc[a] = fma(JxW, k.F1[a], fma(Wi, k.F0[a], Facc[a]));
+#pragma unroll
+      for (int ab = 0; ab < VV; ab++) {
+        if (!(KMASK >> ab & 1u)) continue;
+        const int a = ab / NV, b = ab % NV;
+        const int s = slot_of(KMASK, ab);
+        double mj = 0.0;  // multiplies phi_j
+        if (M::CMASK >> ab & 1u) mj = Wi * k.C[a][b];
+        if (M::TMASK >> ab & 1u) mj = fma(JxW, k.T[a][b], mj);
+        const double sj = (M::SMASK >> ab & 1u) ? JxW * k.S[a][b] : 0.0;  // multiplies grad phi_j . grad phi_i
+#pragma unroll
+        for (int j = 0; j < NEN; j++) {
+          double acc = fma(mj, phi_q[j], Kacc[j][s]);
+          if (M::SMASK >> ab & 1u) acc = fma(sj, dot3(dphi[j], dNi), acc);
+          Kacc[j][s] = acc;
+        }
+      }
+    };
+
+    if constexpr (NEN == 4) {
+      // affine map: J, dphi are element constants (evaluated like FEMap does, Appendix B-4)
+      const double dx_dxi = X[1][0] - X[0][0], dx_deta = X[2][0] - X[0][0], dx_dzeta = X[3][0] - X[0][0];
+      const double dy_dxi = X[1][1] - X[0][1], dy_deta = X[2][1] - X[0][1], dy_dzeta = X[3][1] - X[0][1];
+      const double dz_dxi = X[1][2] - X[0][2], dz_deta = X[2][2] - X[0][2], dz_dzeta = X[3][2] - X[0][2];
+      const double jac = dx_dxi * (dy_deta * dz_dzeta - dz_deta * dy_dzeta) + dy_dxi * (dz_deta * dx_dzeta - dx_deta * dz_dzeta) +
+                         dz_dxi * (dx_deta * dy_dzeta - dy_deta * dx_dzeta);
+      const double inv = 1. / jac;
+      double dphi[4][3];
+      dphi[1][0] = (dy_deta * dz_dzeta - dz_deta * dy_dzeta) * inv;
+      dphi[1][1] = (dz_deta * dx_dzeta - dx_deta * dz_dzeta) * inv;
+      dphi[1][2] = (dx_deta * dy_dzeta - dy_deta * dx_dzeta) * inv;
+      dphi[2][0] = (dz_dxi * dy_dzeta - dy_dxi * dz_dzeta) * inv;
+      dphi[2][1] = (dx_dxi * dz_dzeta - dz_dxi * dx_dzeta) * inv;
+      dphi[2][2] = (dy_dxi * dx_dzeta - dx_dxi * dy_dzeta) * inv;
+      dphi[3][0] = (dy_dxi * dz_deta - dz_dxi * dy_deta) * inv;
+      dphi[3][1] = (dz_dxi * dx_deta - dx_dxi * dz_deta) * inv;
+      dphi[3][2] = (dx_dxi * dy_deta - dy_dxi * dx_deta) * inv;
+#pragma unroll
+      for (int d = 0; d < 3; d++) dphi[0][d] = (-dphi[1][d] - dphi[2][d]) - dphi[3][d];
+      // gradients and direction vectors are element constants as well
+      double G[NV][3], GA[NA_][3], dir[M::NDIR][3];
+#pragma unroll
+      for (int a = 0; a < NV; a++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          double g = 0.0;
+          if (M::GRADMASK >> a & 1u) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) g = g + dphi[l][d] * U[a][l];
+          }
+          G[a][d] = g;
+        }
+#pragma unroll
+      for (int m = 0; m < NA_; m++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          double g = 0.0;
+          if (NAUX > 0 && (M::AUXGRADMASK >> m & 1u)) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) g = g + dphi[l][d] * AX[m][l];
+          }
+          GA[m][d] = g;
+        }
+      M::directions(P, G, ef, GA, dir);
+#pragma unroll
+      for (int q = 0; q < NQP; q++) qp_body(q, jac * T.w[q], dphi, dir, true);
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < NQP; q++) {
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // J[c][r] = d x_c / d xi_r
+#pragma unroll
+        for (int n = 0; n < NEN; n++)
+#pragma unroll
+          for (int cc = 0; cc < 3; cc++) {
+            J[cc][0] = J[cc][0] + X[n][cc] * T.dxi[n][q];
+            J[cc][1] = J[cc][1] + X[n][cc] * T.deta[n][q];
+            J[cc][2] = J[cc][2] + X[n][cc] * T.dzeta[n][q];
+          }
+        const double dx_dxi = J[0][0], dx_deta = J[0][1], dx_dzeta = J[0][2];
+        const double dy_dxi = J[1][0], dy_deta = J[1][1], dy_dzeta = J[1][2];
+        const double dz_dxi = J[2][0], dz_deta = J[2][1], dz_dzeta = J[2][2];
+        const double jac = dx_dxi * (dy_deta * dz_dzeta - dz_deta * dy_dzeta) + dy_dxi * (dz_deta * dx_dzeta - dx_deta * dz_dzeta) +
+                           dz_dxi * (dx_deta * dy_dzeta - dy_deta * dx_dzeta);
+        const double inv = 1. / jac;
+        const double dxidx = (dy_deta * dz_dzeta - dz_deta * dy_dzeta) * inv, dxidy = (dz_deta * dx_dzeta - dx_deta * dz_dzeta) * inv,
+                     dxidz = (dx_deta * dy_dzeta - dy_deta * dx_dzeta) * inv;
+        const double detadx = (dz_dxi * dy_dzeta - dy_dxi * dz_dzeta) * inv, detady = (dx_dxi * dz_dzeta - dz_dxi * dx_dzeta) * inv,
+                     detadz = (dy_dxi * dx_dzeta - dx_dxi * dy_dzeta) * inv;
+        const double dzetadx = (dy_dxi * dz_deta - dz_dxi * dy_deta) * inv, dzetady = (dz_dxi * dx_deta - dx_dxi * dz_deta) * inv,
+                     dzetadz = (dx_dxi * dy_deta - dy_dxi * dx_deta) * inv;
+        double dphi[NEN][3];
+#pragma unroll
+        for (int n = 0; n < NEN; n++) {
+          dphi[n][0] = T.dxi[n][q] * dxidx + T.deta[n][q] * detadx + T.dzeta[n][q] * dzetadx;
+          dphi[n][1] = T.dxi[n][q] * dxidy + T.deta[n][q] * detady + T.dzeta[n][q] * dzetady;
+          dphi[n][2] = T.dxi[n][q] * dxidz + T.deta[n][q] * detadz + T.dzeta[n][q] * dzetadz;
+        }
+        qp_body(q, jac * T.w[q], dphi, nullptr, false);
+      }
+    }
+
+    // stage my row
+#pragma unroll
+    for (int j = 0; j < NEN; j++)
+#pragma unroll
+      for (int s = 0; s < NKV; s++) stageK[((size_t)j * NKV + s) * PAIRS + tid] = Kacc[j][s];
+#pragma unroll
+    for (int a = 0; a < NV; a++) stageF[a * PAIRS + tid] = Facc[a];
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ phase 2: one block per thread
+  const int blk0 = s_rowptr[0], nblk = s_rowptr[nnode] - blk0;
+  for (int b = tid; b < nblk; b += PAIRS) {
+    const int B = blk0 + b;
+    int lo = 0, hi = nnode;  // largest r with s_rowptr[r] <= B
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_rowptr[mid] <= B) lo = mid; else hi = mid;
+    }
+    const int L = s_rowptr[lo + 1] - s_rowptr[lo], kk = B - s_rowptr[lo];
+    double acc[NKV > 0 ? NKV : 1];
+#pragma unroll
+    for (int s = 0; s < NKV; s++) acc[s] = 0.0;
+    const int c0 = A.cptr[B], c1 = A.cptr[B + 1];
+    for (int c = c0; c < c1; c++) {
+      const unsigned code = A.clist[c];
+      const double* src = stageK + ((size_t)(code >> 12) * NKV) * PAIRS + (code & 0xfffu);
+#pragma unroll
+      for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * PAIRS];
+    }
+    double* dst = A.val + (size_t)s_rowptr[lo] * VV + kk;
+#pragma unroll
+    for (int ab = 0; ab < VV; ab++) dst[(size_t)ab * L] = (KMASK >> ab & 1u) ? acc[slot_of(KMASK, ab)] : 0.0;
+  }
+  for (int t = tid; t < nnode * NV; t += PAIRS) {
+    const int r = t / NV, a = t - r * NV;
+    const int q0 = A.n2e_ptr[node0 + r] - pair0, q1 = A.n2e_ptr[node0 + r + 1] - pair0;
+    double f = 0.0;
+    for (int q = q0; q < q1; q++) f += stageF[a * PAIRS + q];
+    A.rhs[(size_t)(node0 + r) * NV + a] = f;
+  }
+}
+
+// diagonal of K -> dinv (point Jacobi) ; one thread per owned node
+__global__ void k_extract_diag(int n_owned, int nv, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ diag_blk,
+                               const double* __restrict__ val, double* __restrict__ dinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_owned) return;
+  const int r0 = rowptr[i], L = rowptr[i + 1] - r0, k = diag_blk[i] - r0;
+  for (int a = 0; a < nv; a++) dinv[(size_t)i * nv + a] = 1.0 / val[(size_t)r0 * nv * nv + (size_t)(a * nv + a) * L + k];
+}
+
+// ---------------------------------------------------------------------------------- host launchers
+static void fill_pulse(Pulse& o, const double* p) { o.cM = p[0]; o.c0 = p[1]; o.c1 = p[2]; }
+static void fill_sd(StepDecay& o, const double* p) { o.cM = p[0]; o.c0 = p[1]; o.c1 = p[2]; o.slope = p[0] / (p[2] - p[1]); }
+static void fill_tr(Trapezoid& o, const double* p) {
+  o.cM = p[0]; o.c0 = p[1]; o.c1 = p[2]; o.c2 = p[3]; o.c3 = p[4];
+  o.up = p[0] / (p[2] - p[1]); o.dn = p[0] / (p[4] - p[3]);
+}
+
+template <class M, int NEN, int PAIRS>
+static int launch_t(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
+  constexpr unsigned KMASK = M::CMASK | M::SMASK | M::TMASK;
+  const size_t smem = ((size_t)NEN * popc(KMASK) + M::NV) * PAIRS * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    RDC_CUDA(cudaFuncSetAttribute(k_assemble<M, NEN, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_assemble<M, NEN, PAIRS><<<c->ncta, PAIRS, smem, c->stream>>>(A, P);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <class M>
+static int launch_m(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
+  if (c->etype == RDC_TET4) {
+    if (c->S.pairs_per_cta == 256) return launch_t<M, 4, 256>(c, A, P);
+    return launch_t<M, 4, 128>(c, A, P);
+  }
+  return launch_t<M, 8, 128>(c, A, P);
+}
+
+// pairs per assembly CTA (= block size); bounded by the shared-memory stage of nen*nkv+v doubles per pair
+int pairs_per_cta_for(int model, int etype) {
+  const bool v5 = (model == RDC_PIHNA || model == RDC_PROTEAS);
+  if (etype == RDC_TET4) return v5 ? 128 : 256;
+  return 128;
+}
+
+int launch_assemble(rdc_ctx* c) {
+  AsmArgs A;
+  A.conn = c->d_conn; A.xyz4 = c->d_xyz; A.u_old = c->d_uold; A.efield = c->d_efield;
+  A.aux0 = nullptr; A.aux1 = nullptr;
+  A.n2e_ptr = c->d_n2e_ptr; A.pair = c->d_pair; A.rowptr = c->d_rowptr; A.cta_node = c->d_cta_node;
+  A.cptr = c->d_cptr; A.clist = c->d_clist; A.val = c->d_val; A.rhs = c->d_rhs;
+  const double* p = c->params.data();
+  const double h = c->dt / 2.0;
+  switch (c->model) {
+    case RDC_ADPM: {
+      AdpmParams P;
+      P.dt2 = h;
+      fill_pulse(P.decay_PrP, p + ADPM_DECAY_PRP);
+      P.decay_PrP.cM = p[ADPM_DECAY_PRP] * pow(c->time, p[ADPM_GAMMA]);  // adpm.C:369
+      fill_pulse(P.diffuse_A, p + ADPM_DIFFUSE_AB); fill_pulse(P.taxis1_A, p + ADPM_TAXIS1_AB);
+      fill_pulse(P.taxis2_A, p + ADPM_TAXIS2_AB); fill_sd(P.produce_A, p + ADPM_PRODUCE_AB);
+      fill_tr(P.transform_A, p + ADPM_TRANSFORM_AB); fill_pulse(P.decay_A, p + ADPM_DECAY_AB);
+      fill_pulse(P.diffuse_T, p + ADPM_DIFFUSE_TAU); fill_pulse(P.taxis1_T, p + ADPM_TAXIS1_TAU);
+      fill_pulse(P.taxis2_T, p + ADPM_TAXIS2_TAU); fill_sd(P.produce_T, p + ADPM_PRODUCE_TAU);
+      fill_tr(P.transform_T, p + ADPM_TRANSFORM_TAU); fill_pulse(P.decay_T, p + ADPM_DECAY_TAU);
+      P.omega_A = cos(p[ADPM_ANGLE_AB]); P.omega_T = cos(p[ADPM_ANGLE_TAU]);
+      if (!c->d_efield) { c->err = "ADPM needs the tract vectors (rdc_set_elem_field slot 0)"; return RDC_E_STATE; }
+      return launch_m<Adpm>(c, A, P);
+    }
+    case RDC_PIHNA: {
+      PihnaParams P;
+      P.dt2 = h;
+      P.Lambda_k = p[PIHNA_LAMBDA_K]; P.Kappa_k = p[PIHNA_KAPPA_K]; P.Kappa_a = p[PIHNA_KAPPA_A]; P.ek = p[PIHNA_EK];
+      P.nec_c = p[PIHNA_NECROSIS_C] / P.Kappa_k; P.nec_h = p[PIHNA_NECROSIS_H] / P.Kappa_k; P.nec_v = p[PIHNA_NECROSIS_V] / P.Kappa_k;
+      P.dif_c = p[PIHNA_DIFFUSE_C]; P.tax_c = p[PIHNA_TAXIS_C]; P.dif_h = p[PIHNA_DIFFUSE_H]; P.tax_h = p[PIHNA_TAXIS_H];
+      P.prod_c = p[PIHNA_PRODUCE_C]; P.c2h = p[PIHNA_SWITCH_C2H]; P.h2c = p[PIHNA_SWITCH_H2C]; P.h2n = p[PIHNA_SWITCH_H2N];
+      P.dif_v = p[PIHNA_DIFFUSE_V]; P.tax_v = p[PIHNA_TAXIS_V]; P.prod_v = p[PIHNA_PRODUCE_V];
+      P.sec_c = p[PIHNA_SECRETE_A_C]; P.sec_h = p[PIHNA_SECRETE_A_H]; P.upt_v = p[PIHNA_UPTAKE_A_V]; P.dec_a = p[PIHNA_DECAY_A];
+      return launch_m<Pihna>(c, A, P);
+    }
+    case RDC_RIPF: {
+      RipfParams P;
+      P.dt2 = h;
+      P.VF_s = p[RIPF_VF_STROMA]; P.VF_p = p[RIPF_VF_PARENCHYMA]; P.VF_e = p[RIPF_VF_EXPONENT]; P.VF_min = p[RIPF_VF_MIN_VACANT];
+      P.phi_cc_B = p[RIPF_PHI_CC_B]; P.phi_cc_D = p[RIPF_PHI_CC_D]; P.phi_cc = p[RIPF_PHI_CC];
+      P.phi_fb_B = p[RIPF_PHI_FB_B]; P.phi_fb_D = p[RIPF_PHI_FB_D]; P.phi_fb = p[RIPF_PHI_FB]; P.phi_tol = p[RIPF_PHI_TOL];
+      P.kappa = p[RIPF_KAPPA]; P.kappa_RT_c = p[RIPF_KAPPA_RT_C]; P.delta = p[RIPF_DELTA];
+      P.delta_RT_a = p[RIPF_DELTA_RT_A]; P.delta_RT_b = p[RIPF_DELTA_RT_B];
+      P.lambda = p[RIPF_LAMBDA];
+      P.lambda_RT_r = p[RIPF_LAMBDA_RT_R] != 0.0 ? p[RIPF_LAMBDA_RT_R] : (double)c->ripf_rt_max;  // ripf.C:398-399
+      P.lambda_HU_r = p[RIPF_LAMBDA_HU_R]; P.omicro = p[RIPF_OMICRO];
+      P.omicro_RT_r = p[RIPF_OMICRO_RT_R] != 0.0 ? p[RIPF_OMICRO_RT_R] : (double)c->ripf_rt_max;  // ripf.C:402-403
+      P.omicro_fb_b = p[RIPF_OMICRO_FB_B]; P.omega = p[RIPF_OMEGA]; P.diffusion = p[RIPF_DIFFUSION];
+      P.haptotaxis = p[RIPF_HAPTOTAXIS]; P.radiotaxis = p[RIPF_RADIOTAXIS];
+      if (!c->d_rt || !c->ripf_primed) {
+        c->err = "RIPF needs the RT dose field (rdc_set_nodal_field slot 0) and the pre-loop rdc_clamp (ripf.C:53)";
+        return RDC_E_STATE;
+      }
+      A.aux0 = c->d_td; A.aux1 = c->d_rt;
+      return launch_m<Ripf>(c, A, P);
+    }
+    case RDC_PROTEAS: {
+      ProteasParams P;
+      P.dt2 = h;
+      P.T_max = p[PROTEAS_T_MAX]; P.RT_max = p[PROTEAS_RT_MAX]; P.rho_h = p[PROTEAS_RHO_H]; P.u_h = p[PROTEAS_U_H];
+      P.delta_h = p[PROTEAS_DELTA_H]; P.a_RT_h = p[PROTEAS_A_RT_H]; P.b_RT_h = p[PROTEAS_B_RT_H]; P.nu_h = p[PROTEAS_NU_H];
+      P.D_c = p[PROTEAS_D_C]; P.D_c_h = p[PROTEAS_D_C_H]; P.rho_c = p[PROTEAS_RHO_C]; P.u_c = p[PROTEAS_U_C];
+      P.delta_c = p[PROTEAS_DELTA_C]; P.a_RT_c = p[PROTEAS_A_RT_C]; P.b_RT_c = p[PROTEAS_B_RT_C]; P.nu_c = p[PROTEAS_NU_C];
+      P.psi_n = p[PROTEAS_PSI_N]; P.k_n = p[PROTEAS_K_N]; P.u_n = p[PROTEAS_U_N]; P.rho_v = p[PROTEAS_RHO_V]; P.nu_v = p[PROTEAS_NU_V];
+      P.D_e = p[PROTEAS_D_E]; P.rho_e = p[PROTEAS_RHO_E]; P.u_e = p[PROTEAS_U_E]; P.xi_e = p[PROTEAS_XI_E];
+      P.p_RT_e = p[PROTEAS_P_RT_E]; P.psi_e = p[PROTEAS_PSI_E];
+      if (!c->d_aux) { c->err = "PROTEAS needs the AUX field (rdc_set_nodal_field slot 0)"; return RDC_E_STATE; }
+      A.aux0 = c->d_aux;
+      return launch_m<Proteas>(c, A, P);
+    }
+    case RDC_HCC: {
+      HccParams P;
+      P.dt2 = h;
+      P.Lambda_k = p[HCC_LAMBDA_K]; P.Kappa_k = p[HCC_KAPPA_K]; P.ek = p[HCC_EK]; P.produce_l = p[HCC_PRODUCE_L];
+      P.diffuse_c = p[HCC_DIFFUSE_C]; P.mechano_c = p[HCC_MECHANO_C]; P.produce_c = p[HCC_PRODUCE_C];
+      P.nec_l = p[HCC_NECROSIS_L] / P.Kappa_k; P.nec_c = p[HCC_NECROSIS_C] / P.Kappa_k;
+      return launch_m<Hcc>(c, A, P);
+    }
+  }
+  c->err = "unknown model";
+  return RDC_E_ARG;
+}
+
+int launch_extract_diag(rdc_ctx* c) {
+  const int n = c->S.n_owned;
+  k_extract_diag<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->nv, c->d_rowptr, c->d_diag_blk, c->d_val, c->d_dinv);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rdc

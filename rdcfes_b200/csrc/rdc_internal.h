@@ -1,0 +1,143 @@
+// rdc_internal.h -- context layout shared by setup.cpp (host), assemble.cu, solver.cu and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rdc.h"
+
+#define RDC_MAX_NEN 8
+#define RDC_MAX_QP 8
+
+namespace rdc {
+
+// reference-element tables, computed on the host exactly like libMesh
+// evaluates them (phi0 = 1 - xi - eta - zeta, left to right) and copied to __constant__ memory.
+struct FeTable {
+  int nen, nqp;
+  double w[RDC_MAX_QP];
+  double phi[RDC_MAX_NEN][RDC_MAX_QP];
+  double dxi[RDC_MAX_NEN][RDC_MAX_QP], deta[RDC_MAX_NEN][RDC_MAX_QP], dzeta[RDC_MAX_NEN][RDC_MAX_QP];
+};
+void fe_table_fill(FeTable* T, int elem_type);
+
+struct NcclApi;  // comm.cpp
+
+// Host-side result of the one-time set-up (partition, numbering, pattern, assembly maps).
+struct HostSetup {
+  int nen = 0, nv = 0;
+  int rank = 0, nranks = 1;
+  int64_t N_glob = 0, E_glob = 0;
+  int32_t n_owned = 0, n_ghost = 0, n_loc = 0;   // local node counts (owned first, then ghosts)
+  int64_t E_loc = 0;
+  std::vector<int32_t> loc2glob;                 // [n_loc]
+  std::vector<int32_t> glob2loc;                 // [N_glob], -1 when not present on this rank
+  std::vector<int64_t> elem_glob;                // [E_loc] global element id
+  std::vector<int32_t> conn;                     // [E_loc*nen] local node ids
+  std::vector<int32_t> n2e_ptr;                  // [n_owned+1] into pair[]
+  std::vector<int32_t> pair;                     // [npairs] (local elem << 3) | local node index
+  std::vector<int32_t> rowptr;                   // [n_owned+1] block rows
+  std::vector<int32_t> col;                      // [nnzb] local node ids, sorted per row
+  std::vector<int32_t> diag_blk;                 // [n_owned] block index of the diagonal block
+  std::vector<int32_t> cta_node;                 // [ncta+1] node ranges of the assembly CTAs
+  std::vector<int32_t> cptr;                     // [nnzb+1] into clist
+  std::vector<uint16_t> clist;                   // (j << 12) | pair index inside the CTA
+  int pairs_per_cta = 0;
+  // halo exchange (distributed): ghosts are ordered by owner rank, so each neighbour's ghosts are contiguous
+  std::vector<int> nbr_rank;                     // neighbours
+  std::vector<int32_t> send_ptr, send_idx;       // per neighbour: owned local node ids to send
+  std::vector<int32_t> recv_ptr;                 // per neighbour: ghost range [recv_ptr[k], recv_ptr[k+1]) + n_owned
+  std::vector<int32_t> owner_glob;               // [N_glob] owner rank of every node (empty when nranks == 1)
+};
+
+// partitioner: 0 = METIS k-way on the nodal graph, 1 = recursive coordinate bisection
+int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const int32_t* conn, const double* xyz,
+                int rank, int nranks, int partitioner, int pairs_per_cta, std::string& err);
+
+}  // namespace rdc
+
+struct SolverWork;  // solver.cu
+
+struct rdc_ctx {
+  int model = 0, etype = 0, nen = 0, nv = 0, nqp = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  rdc::HostSetup S;
+  std::vector<int32_t> dof_base;     // [N_glob] global dof id of var 0 (identity = nv*node when empty)
+  bool identity_dofs = true;
+  int64_t D_glob = 0;
+  std::vector<double> params;
+  bool have_params = false;
+  double time = 0.0, dt = 0.0;
+
+  // device: mesh + maps
+  int32_t* d_conn = nullptr;
+  double* d_xyz = nullptr;           // [n_loc*4] padded (x,y,z,0): one 32-byte sector per node
+  double* d_efield = nullptr;        // [E_loc*3]
+  int32_t *d_n2e_ptr = nullptr, *d_pair = nullptr, *d_rowptr = nullptr, *d_col = nullptr, *d_diag_blk = nullptr;
+  int32_t *d_cta_node = nullptr, *d_cptr = nullptr;
+  uint16_t* d_clist = nullptr;
+  int32_t* d_dofmap = nullptr;       // [n_loc*nv] global dof id of each local dof (gather/scatter of user vectors)
+  int ncta = 0;
+  int64_t nnzb = 0;
+
+  // device: operator and vectors.  Vectors are [n_loc*nv]: owned part first, ghost part after it.
+  double *d_val = nullptr, *d_rhs = nullptr, *d_dinv = nullptr;
+  double *d_u = nullptr, *d_uold = nullptr, *d_uolder = nullptr;
+  double* d_stage = nullptr;         // [D_glob] staging for user vectors in global dof order
+  bool assembled = false;
+
+  // model state
+  double *d_td = nullptr, *d_rt = nullptr, *d_prev = nullptr;   // RIPF: TD [n_loc*3], RT [n_loc*3], prev [n_owned*3]
+  double* d_aux = nullptr;                                      // PROTEAS AUX [n_loc*2]
+  int ripf_rt_max = 0;
+  bool ripf_primed = false;
+
+  // solver
+  SolverWork* work = nullptr;
+
+  // comm
+  rdc::NcclApi* nccl = nullptr;
+  void* comm = nullptr;              // ncclComm_t
+  int32_t* d_send_idx = nullptr;
+  double* d_sendbuf = nullptr;
+
+  // stats
+  rdc_stats st = {};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+};
+
+namespace rdc {
+// assemble.cu
+int launch_assemble(rdc_ctx* c);
+int launch_extract_diag(rdc_ctx* c);
+int upload_fe_tables();
+// solver.cu
+int solver_init(rdc_ctx* c);
+void solver_free(rdc_ctx* c);
+int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int restart, int* its, double* res);
+int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done = false);
+int launch_clamp(rdc_ctx* c);
+int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc);     // dst_loc[l] = src[dofmap[l]]
+int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob);    // owned part only
+int halo_exchange(rdc_ctx* c, double* x);                                   // fills the ghost part of x
+int allreduce_sum(rdc_ctx* c, double* d_buf, int n);
+int allreduce_max(rdc_ctx* c, double* d_buf, int n);
+// comm.cpp
+int comm_unique_id(void* out128, std::string& err);
+int comm_init(rdc_ctx* c, const void* uid, std::string& err);
+void comm_destroy(rdc_ctx* c);
+}  // namespace rdc
+
+#define RDC_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+      return RDC_E_CUDA;                                                                 \
+    }                                                                                    \
+  } while (0)

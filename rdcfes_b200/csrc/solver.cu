@@ -1,0 +1,793 @@
+// solver.cu -- block-CSR SpMV and the device-resident Krylov solvers (GMRES(m), CG, BiCGStab) with
+// Jacobi preconditioning; check_solution kernels; halo exchange + all-reduce plumbing.
+//
+// Replaces PetscLinearSolver::solve -> KSPSolve inside TransientLinearImplicitSystem::solve()
+// (adpm.C:74, pihna.C:80, ripf.C:83, proteas.C:78, coupled_hcc.C:114) and the per-model check_solution
+// (adpm.C:654-688, pihna.C:760-803, proteas.C:707-750, coupled_hcc.C:695-731, ripf.C:675-775).
+// Semantics kept from the libMesh/PETSc defaults: restarted GMRES with
+// classical Gram-Schmidt, LEFT preconditioning, convergence on the preconditioned residual
+// ||B r|| <= max(rtol ||B b||, 1e-50), initial guess = current solution.
+//
+// Everything stays on the device: dot products are warp-shuffle + fixed-order block/grid reductions
+// (bit-reproducible), the Hessenberg/Givens update is a one-thread kernel, and every kernel of an
+// iteration returns immediately once the device-side "converged" flag is set, so the host only polls
+// that flag every few iterations instead of synchronising per dot product.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "rdc_internal.h"
+
+namespace rdc {
+
+static constexpr int RED_BLOCKS = 592;   // 4 CTAs per SM on 148 SMs
+static constexpr int RED_THREADS = 256;
+static constexpr int MD_CHUNK = 8;       // vectors per multi-dot pass
+
+}  // namespace rdc
+
+struct SolverWork {
+  int restart_cap = 0;
+  size_t vec_len = 0;        // n_loc * nv
+  double* V = nullptr;       // [(restart_cap+1)] basis vectors, each vec_len (ghost space included)
+  double* t0 = nullptr;      // work vectors
+  double* t1 = nullptr;
+  double* t2 = nullptr;
+  double* t3 = nullptr;
+  double* t4 = nullptr;
+  double* partial = nullptr; // [RED_BLOCKS * (MD_CHUNK+1)]
+  unsigned* counter = nullptr;
+  double* h = nullptr;       // [restart_cap + 2] dots of the current column (+ norm^2)
+  double* H = nullptr;       // [(restart_cap+1) * restart_cap] column-major Hessenberg after rotations
+  double* cs = nullptr; double* sn = nullptr; double* g = nullptr; double* y = nullptr;
+  double* scal = nullptr;    // device scalars: [0] res, [1] target, [2] beta, [3] 1/hnorm, [4..] CG/BiCGStab scalars
+  int* state = nullptr;      // [0] done, [1] total its, [2] j in cycle, [3] breakdown
+  double* h_scal = nullptr;  // pinned mirrors
+  int* h_state = nullptr;
+  static constexpr int MAX_EV = 512;
+  cudaEvent_t ev[2 * MAX_EV];
+  int n_ev_used = 0;
+};
+
+namespace rdc {
+
+// ------------------------------------------------------------------------------------------ SpMV
+// Half-warp per block row; lane k owns block k of the row (row-local SoA layout -> every load of a
+// half-warp is one contiguous segment).  rowscale != nullptr fuses the Jacobi scaling: y = D^-1 (A x).
+template <int NV>
+__global__ void __launch_bounds__(256) k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                              const double* __restrict__ val, const double* __restrict__ x,
+                                              double* __restrict__ y, const double* __restrict__ rowscale,
+                                              const int* __restrict__ done) {
+  if (done && *done) return;
+  const int lane16 = threadIdx.x & 15;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 4);
+  double acc[NV];
+#pragma unroll
+  for (int a = 0; a < NV; a++) acc[a] = 0.0;
+  if (row < n_rows) {
+    const int r0 = rowptr[row], L = rowptr[row + 1] - r0;
+    const double* v0 = val + (size_t)r0 * (NV * NV);
+    for (int k = lane16; k < L; k += 16) {
+      const int c = col[r0 + k];
+      double xv[NV];
+#pragma unroll
+      for (int b = 0; b < NV; b++) xv[b] = x[(size_t)c * NV + b];
+#pragma unroll
+      for (int a = 0; a < NV; a++)
+#pragma unroll
+        for (int b = 0; b < NV; b++) acc[a] = fma(v0[(size_t)(a * NV + b) * L + k], xv[b], acc[a]);
+    }
+  }
+#pragma unroll
+  for (int off = 8; off > 0; off >>= 1)
+#pragma unroll
+    for (int a = 0; a < NV; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off, 16);
+  if (row < n_rows && lane16 == 0) {
+#pragma unroll
+    for (int a = 0; a < NV; a++) {
+      const size_t o = (size_t)row * NV + a;
+      y[o] = rowscale ? acc[a] * rowscale[o] : acc[a];
+    }
+  }
+}
+
+int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done) {
+  const int n = c->S.n_owned;
+  const int* done = (check_done && c->work) ? c->work->state : nullptr;
+  const unsigned grid = (unsigned)(((size_t)n * 16 + 255) / 256);
+  // every SpMV launch of a solve is bracketed by its own event pair (summed after the solve) so that the
+  // roofline of the dominant kernel is measured live, inside the timed step
+  SolverWork* W = c->work;
+  const bool timed = check_done && W && W->n_ev_used < SolverWork::MAX_EV;
+  if (timed) cudaEventRecord(W->ev[2 * W->n_ev_used], c->stream);
+  if (c->nv == 3) k_spmv<3><<<grid, 256, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, done);
+  else k_spmv<5><<<grid, 256, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, done);
+  if (timed) { cudaEventRecord(W->ev[2 * W->n_ev_used + 1], c->stream); W->n_ev_used++; }
+  c->st.kernel_launches++;
+  c->st.n_spmv++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------- reductions (fixed order)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// block-reduce NV values, write partial[blockIdx][k]; the last block to finish adds the partials of all
+// blocks in index order and writes out[k] -- one launch, deterministic.
+template <int NVAL>
+__device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double* partial, unsigned* counter, double* out) {
+  __shared__ double s_red[RED_THREADS / 32][NVAL];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NVAL; k++) {
+    const double w = warp_sum(v[k]);
+    if (lane == 0) s_red[wid][k] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < NVAL && threadIdx.x < nval) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < RED_THREADS / 32; w++) s += s_red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * NVAL + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < NVAL && threadIdx.x < nval) {
+      double s = 0.0;
+      for (unsigned b = 0; b < gridDim.x; b++) s += partial[(size_t)b * NVAL + threadIdx.x];
+      out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// out[k] = <V_k, w> for k < nvec (nvec <= MD_CHUNK) and, when with_norm, out[nvec] = <w, w>
+__global__ void __launch_bounds__(RED_THREADS) k_multidot(size_t n, int nvec, const double* __restrict__ V, size_t ldv,
+                                                          const double* __restrict__ w, int with_norm, double* partial,
+                                                          unsigned* counter, double* out, const int* __restrict__ done) {
+  if (done && *done) return;
+  double acc[MD_CHUNK + 1];
+#pragma unroll
+  for (int k = 0; k <= MD_CHUNK; k++) acc[k] = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double wi = w[i];
+#pragma unroll
+    for (int k = 0; k < MD_CHUNK; k++)
+      if (k < nvec) acc[k] = fma(V[(size_t)k * ldv + i], wi, acc[k]);
+    if (with_norm) acc[MD_CHUNK] = fma(wi, wi, acc[MD_CHUNK]);
+  }
+  if (with_norm) {  // place the norm right after the dots
+    double nn = acc[MD_CHUNK];
+#pragma unroll
+    for (int k = 0; k < MD_CHUNK; k++)
+      if (k == nvec) acc[k] = nn;
+    if (nvec == MD_CHUNK) acc[MD_CHUNK] = nn;
+  }
+  grid_reduce<MD_CHUNK + 1>(acc, nvec + (with_norm ? 1 : 0), partial, counter, out);
+}
+
+// w -= sum_k h[k] V_k (k < nvec) ; out[0] = ||w||^2
+__global__ void __launch_bounds__(RED_THREADS) k_gs_update(size_t n, int nvec, const double* __restrict__ V, size_t ldv,
+                                                           double* __restrict__ w, const double* __restrict__ h,
+                                                           double* partial, unsigned* counter, double* out,
+                                                           const int* __restrict__ done) {
+  if (done && *done) return;
+  double acc[1] = {0.0};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double wi = w[i];
+    for (int k = 0; k < nvec; k++) wi = fma(-h[k], V[(size_t)k * ldv + i], wi);
+    w[i] = wi;
+    acc[0] = fma(wi, wi, acc[0]);
+  }
+  grid_reduce<1>(acc, 1, partial, counter, out);
+}
+
+// x[i] = alpha_dev[0] * x[i]
+__global__ void k_scale_dev(size_t n, double* __restrict__ x, const double* __restrict__ alpha, const int* __restrict__ done) {
+  if (done && *done) return;
+  const double a = *alpha;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= a;
+}
+
+// x += sum_k y[k] V_k, k < *ny
+__global__ void k_update_x(size_t n, const int* __restrict__ ny, const double* __restrict__ V, size_t ldv,
+                           const double* __restrict__ y, double* __restrict__ x) {
+  const int m = *ny;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double xi = x[i];
+    for (int k = 0; k < m; k++) xi = fma(y[k], V[(size_t)k * ldv + i], xi);
+    x[i] = xi;
+  }
+}
+
+// r = scale .* (b - t)   (t = A x)
+__global__ void k_residual(size_t n, const double* __restrict__ b, const double* __restrict__ t, const double* __restrict__ scale,
+                           double* __restrict__ r) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    r[i] = scale ? (b[i] - t[i]) * scale[i] : (b[i] - t[i]);
+}
+__global__ void k_mul(size_t n, const double* __restrict__ a, const double* __restrict__ s, double* __restrict__ o) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    o[i] = s ? a[i] * s[i] : a[i];
+}
+
+// ---- GMRES small kernels (one thread) ----
+// start of a cycle: beta = sqrt(nrm2) ; g = (beta,0,..) ; scal[3] = 1/beta ; convergence test on beta
+__global__ void k_gmres_begin(const double* nrm2, double* g, double* scal, int* state, int m) {
+  const double beta = sqrt(nrm2[0]);
+  for (int k = 0; k <= m; k++) g[k] = 0.0;
+  g[0] = beta;
+  scal[0] = beta;
+  scal[2] = beta;
+  scal[3] = beta != 0.0 ? 1.0 / beta : 0.0;
+  state[2] = 0;
+  if (beta <= scal[1]) state[0] = 1;
+}
+// end of inner iteration j: h[0..j] dots, hn2 = ||w||^2 -> Hessenberg column, Givens, residual estimate
+__global__ void k_gmres_givens(int j, int m, const double* h, const double* hn2, double* H, double* cs, double* sn, double* g,
+                               double* scal, int* state) {
+  if (state[0]) return;
+  const double hn = sqrt(hn2[0]);
+  double* Hj = H + (size_t)j * (m + 1);
+  for (int k = 0; k <= j; k++) Hj[k] = h[k];
+  Hj[j + 1] = hn;
+  for (int k = 0; k < j; k++) {
+    const double a = Hj[k], b = Hj[k + 1];
+    Hj[k] = cs[k] * a + sn[k] * b;
+    Hj[k + 1] = -sn[k] * a + cs[k] * b;
+  }
+  const double a = Hj[j], b = Hj[j + 1];
+  const double r = hypot(a, b);
+  cs[j] = r == 0.0 ? 1.0 : a / r;
+  sn[j] = r == 0.0 ? 0.0 : b / r;
+  Hj[j] = r;
+  Hj[j + 1] = 0.0;
+  g[j + 1] = -sn[j] * g[j];
+  g[j] = cs[j] * g[j];
+  const double res = fabs(g[j + 1]);
+  scal[0] = res;
+  scal[3] = hn != 0.0 ? 1.0 / hn : 0.0;
+  state[1] += 1;
+  state[2] = j + 1;
+  if (!(res == res)) { state[0] = 1; state[3] = 1; }           // NaN: breakdown
+  else if (res <= scal[1] || hn == 0.0) state[0] = 1;
+}
+// y = H^-1 g for the first state[2] columns
+__global__ void k_gmres_backsolve(int m, const double* H, const double* g, double* y, const int* state) {
+  const int j = state[2];
+  for (int k = j - 1; k >= 0; k--) {
+    double s = g[k];
+    for (int l = k + 1; l < j; l++) s -= H[(size_t)l * (m + 1) + k] * y[l];
+    y[k] = s / H[(size_t)k * (m + 1) + k];
+  }
+}
+__global__ void k_set_target(const double* nrm2, double rtol, double* scal) {
+  const double bn = sqrt(nrm2[0]);
+  scal[1] = fmax(rtol * bn, 1e-50);
+  scal[5] = bn;
+}
+
+// ------------------------------------------------------------------------------ check_solution
+// adpm.C:675-677 and siblings: if (u < 0) u = 0
+__global__ void k_clamp_nonneg(size_t n, double* __restrict__ u) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = u[i];
+    if (v < 0.0) u[i] = 0.0;
+  }
+}
+// ripf.C:709-760 for every local node (ghosts included for RT_total; u/prev/TD on owned nodes)
+__global__ void __launch_bounds__(RED_THREADS) k_ripf_check(int n_owned, int n_loc, double* __restrict__ u, double* __restrict__ prev,
+                                                            double* __restrict__ td, double* __restrict__ rt, double HU_min,
+                                                            double HU_max, double bf, double ff, int day, double DT_R,
+                                                            double* partial, unsigned* counter, double* out) {
+  double mx[1] = {-1.0};
+  const double tf = bf + ff;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < n_loc; n += gridDim.x * blockDim.x) {
+    const double RT_broad = rt[(size_t)n * 3], RT_focus = rt[(size_t)n * 3 + 1];
+    double RT_total;
+    if (day < bf) RT_total = RT_broad / bf * (day + 1);
+    else if (day < tf) RT_total = RT_focus / ff * ((day + 1) - bf) + RT_broad;
+    else RT_total = RT_broad + RT_focus;
+    rt[(size_t)n * 3 + 2] = RT_total;
+    if (n < n_owned) {
+      mx[0] = fmax(mx[0], RT_total);
+      const double s0 = u[(size_t)n * 3], s1 = u[(size_t)n * 3 + 1], s2 = u[(size_t)n * 3 + 2];
+      double HU = s0, cc = s1, fb = s2;
+      if (HU < HU_min) HU = HU_min; else if (HU > HU_max) HU = HU_max;
+      if (cc < 0.0) cc = 0.0;
+      if (fb < 0.0) fb = 0.0;
+      td[(size_t)n * 3] = (HU - prev[(size_t)n * 3]) * DT_R;
+      td[(size_t)n * 3 + 1] = (cc - prev[(size_t)n * 3 + 1]) * DT_R;
+      td[(size_t)n * 3 + 2] = (fb - prev[(size_t)n * 3 + 2]) * DT_R;
+      prev[(size_t)n * 3] = s0; prev[(size_t)n * 3 + 1] = s1; prev[(size_t)n * 3 + 2] = s2;
+      u[(size_t)n * 3] = HU; u[(size_t)n * 3 + 1] = cc; u[(size_t)n * 3 + 2] = fb;
+    }
+  }
+  // max-reduce (order independent)
+  __shared__ double s_mx[RED_THREADS / 32];
+  __shared__ bool s_last;
+  double m = mx[0];
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < RED_THREADS / 32; w++) m = fmax(m, s_mx[w]);
+    partial[blockIdx.x] = m;
+    __threadfence();
+    s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double g = -1.0;
+    for (unsigned b = 0; b < gridDim.x; b++) g = fmax(g, partial[b]);
+    out[0] = g;
+    *counter = 0u;
+  }
+}
+
+// ------------------------------------------------------------------- user vector gather / scatter
+__global__ void k_gather(size_t n, const int32_t* __restrict__ map, const double* __restrict__ src, double* __restrict__ dst) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[map[i]];
+}
+__global__ void k_scatter(size_t n, const int32_t* __restrict__ map, const double* __restrict__ src, double* __restrict__ dst) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[map[i]] = src[i];
+}
+// pack nv values of each listed node
+__global__ void k_pack(size_t n_nodes, int nv, const int32_t* __restrict__ idx, const double* __restrict__ x, double* __restrict__ buf) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_nodes * nv; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t node = i / nv, a = i - node * nv;
+    buf[i] = x[(size_t)idx[node] * nv + a];
+  }
+}
+
+static inline unsigned grid_for(size_t n) {
+  size_t g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc) {
+  const size_t n = (size_t)c->S.n_loc * c->nv;
+  k_gather<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_dofmap, src_glob, dst_loc);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob) {
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  k_scatter<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_dofmap, src_loc, dst_glob);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack(rdc_ctx* c, const double* x, int ncomp) {
+  const size_t n = c->S.send_idx.size();
+  if (n == 0) return 0;
+  k_pack<<<grid_for(n * ncomp), 256, 0, c->stream>>>(n, ncomp, c->d_send_idx, x, c->d_sendbuf);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_clamp(rdc_ctx* c) {
+  SolverWork* W = c->work;
+  if (c->model == RDC_RIPF) {
+    const double* p = c->params.data();
+    const int day = (int)floor(c->time);  // ripf.C:705
+    k_ripf_check<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(c->S.n_owned, c->S.n_loc, c->d_u, c->d_prev, c->d_td, c->d_rt,
+                                                           p[RIPF_HU_MIN], p[RIPF_HU_MAX], p[RIPF_RT_BROAD_FRAC],
+                                                           p[RIPF_RT_FOCUS_FRAC], day, 1.0 / c->dt, W->partial, W->counter, W->h);
+    c->st.kernel_launches++;
+    RDC_CUDA(cudaGetLastError());
+    int rc = allreduce_max(c, W->h, 1);
+    if (rc) return rc;
+    RDC_CUDA(cudaMemcpyAsync(W->h_scal, W->h, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RDC_CUDA(cudaStreamSynchronize(c->stream));
+    const double mx = W->h_scal[0];
+    c->ripf_rt_max = (int)mx;  // ripf.C:772 (int truncation)
+    c->st.ripf_rt_total_max = c->ripf_rt_max;
+    c->ripf_primed = true;
+    if (mx <= 0.0) { c->err = "RT_total_max <= 0 (ripf.C:773)"; return RDC_E_MODEL; }
+    // ghosts of TD are needed by the next assembly
+    if (c->S.nranks > 1) { rc = halo_exchange(c, c->d_td); if (rc) return rc; }
+    return 0;
+  }
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  k_clamp_nonneg<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_u);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------- solver work space
+int solver_init(rdc_ctx* c) {
+  SolverWork* W = new SolverWork();
+  c->work = W;
+  W->vec_len = (size_t)c->S.n_loc * c->nv;
+  const size_t vb = W->vec_len * sizeof(double);
+  RDC_CUDA(cudaMalloc(&W->t0, vb)); RDC_CUDA(cudaMalloc(&W->t1, vb));
+  RDC_CUDA(cudaMemsetAsync(W->t0, 0, vb, c->stream)); RDC_CUDA(cudaMemsetAsync(W->t1, 0, vb, c->stream));
+  RDC_CUDA(cudaMalloc(&W->partial, sizeof(double) * RED_BLOCKS * (MD_CHUNK + 1)));
+  RDC_CUDA(cudaMalloc(&W->counter, sizeof(unsigned)));
+  RDC_CUDA(cudaMemsetAsync(W->counter, 0, sizeof(unsigned), c->stream));
+  RDC_CUDA(cudaMalloc(&W->scal, sizeof(double) * 32));
+  RDC_CUDA(cudaMemsetAsync(W->scal, 0, sizeof(double) * 32, c->stream));
+  RDC_CUDA(cudaMalloc(&W->state, sizeof(int) * 8));
+  RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
+  RDC_CUDA(cudaMallocHost(&W->h_scal, sizeof(double) * 32));
+  RDC_CUDA(cudaMallocHost(&W->h_state, sizeof(int) * 8));
+  RDC_CUDA(cudaMalloc(&W->h, sizeof(double) * 1024));
+  for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) RDC_CUDA(cudaEventCreate(&W->ev[k]));
+  return 0;
+}
+
+static int ensure_gmres(rdc_ctx* c, int restart) {
+  SolverWork* W = c->work;
+  if (restart <= W->restart_cap) return 0;
+  if (W->V) { cudaFree(W->V); cudaFree(W->H); cudaFree(W->cs); cudaFree(W->sn); cudaFree(W->g); cudaFree(W->y); W->V = nullptr; }
+  const size_t vb = W->vec_len * sizeof(double);
+  RDC_CUDA(cudaMalloc(&W->V, vb * (restart + 1)));
+  RDC_CUDA(cudaMemsetAsync(W->V, 0, vb * (restart + 1), c->stream));
+  RDC_CUDA(cudaMalloc(&W->H, sizeof(double) * (restart + 1) * restart));
+  RDC_CUDA(cudaMalloc(&W->cs, sizeof(double) * (restart + 1)));
+  RDC_CUDA(cudaMalloc(&W->sn, sizeof(double) * (restart + 1)));
+  RDC_CUDA(cudaMalloc(&W->g, sizeof(double) * (restart + 2)));
+  RDC_CUDA(cudaMalloc(&W->y, sizeof(double) * (restart + 1)));
+  W->restart_cap = restart;
+  return 0;
+}
+
+static int ensure_extra_vectors(rdc_ctx* c) {
+  SolverWork* W = c->work;
+  if (W->t2) return 0;
+  const size_t vb = W->vec_len * sizeof(double);
+  RDC_CUDA(cudaMalloc(&W->t2, vb)); RDC_CUDA(cudaMalloc(&W->t3, vb)); RDC_CUDA(cudaMalloc(&W->t4, vb));
+  RDC_CUDA(cudaMemsetAsync(W->t2, 0, vb, c->stream)); RDC_CUDA(cudaMemsetAsync(W->t3, 0, vb, c->stream));
+  RDC_CUDA(cudaMemsetAsync(W->t4, 0, vb, c->stream));
+  return 0;
+}
+
+void solver_free(rdc_ctx* c) {
+  SolverWork* W = c->work;
+  if (!W) return;
+  cudaFree(W->V); cudaFree(W->t0); cudaFree(W->t1); cudaFree(W->t2); cudaFree(W->t3); cudaFree(W->t4);
+  cudaFree(W->partial); cudaFree(W->counter); cudaFree(W->h); cudaFree(W->H); cudaFree(W->cs); cudaFree(W->sn);
+  cudaFree(W->g); cudaFree(W->y); cudaFree(W->scal); cudaFree(W->state);
+  cudaFreeHost(W->h_scal); cudaFreeHost(W->h_state);
+  for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) cudaEventDestroy(W->ev[k]);
+  delete W;
+  c->work = nullptr;
+}
+
+// dots of w against V[0..nvec) (+ optional <w,w> appended); result (all-reduced) in W->h[0..]
+static int multidot(rdc_ctx* c, int nvec, const double* V, const double* w, bool with_norm) {
+  SolverWork* W = c->work;
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  int done_cols = 0;
+  while (done_cols < nvec || (nvec == 0 && with_norm && done_cols == 0)) {
+    const int chunk = nvec - done_cols < MD_CHUNK ? nvec - done_cols : MD_CHUNK;
+    const bool last = (done_cols + chunk == nvec);
+    k_multidot<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, V + (size_t)done_cols * W->vec_len, W->vec_len, w,
+                                                         (with_norm && last) ? 1 : 0, W->partial, W->counter,
+                                                         W->h + done_cols, W->state);
+    c->st.kernel_launches++;
+    RDC_CUDA(cudaGetLastError());
+    done_cols += chunk;
+    if (nvec == 0) break;
+  }
+  return allreduce_sum(c, W->h, nvec + (with_norm ? 1 : 0));
+}
+
+static int poll(rdc_ctx* c) {
+  SolverWork* W = c->work;
+  RDC_CUDA(cudaMemcpyAsync(W->h_state, W->state, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
+  RDC_CUDA(cudaMemcpyAsync(W->h_scal, W->scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+  RDC_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// GMRES(m), left Jacobi (or no) preconditioning.  x = c->d_u (initial guess and result), b = c->d_rhs.
+static int gmres(rdc_ctx* c, const double* scale, double rtol, int maxits, int m, int* its_out, double* res_out) {
+  SolverWork* W = c->work;
+  int rc = ensure_gmres(c, m);
+  if (rc) return rc;
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  const size_t ld = W->vec_len;
+  static int sync_every = -1;
+  if (sync_every < 0) { const char* e = getenv("RDC_SYNC_EVERY"); sync_every = e ? atoi(e) : 4; if (sync_every < 1) sync_every = 1; }
+  RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
+  // reference norm ||B b||
+  k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, scale, W->t0);
+  c->st.kernel_launches++;
+  rc = multidot(c, 0, W->t0, W->t0, true);
+  if (rc) return rc;
+  k_set_target<<<1, 1, 0, c->stream>>>(W->h, rtol, W->scal);
+  c->st.kernel_launches++;
+  int its = 0;
+  bool converged = false;
+  while (true) {
+    // v0 = B (b - A x)
+    if ((rc = halo_exchange(c, c->d_u))) return rc;
+    if ((rc = launch_spmv(c, c->d_u, W->t0, nullptr, false))) return rc;
+    k_residual<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, W->t0, scale, W->V);
+    c->st.kernel_launches++;
+    if ((rc = multidot(c, 0, W->V, W->V, true))) return rc;
+    k_gmres_begin<<<1, 1, 0, c->stream>>>(W->h, W->g, W->scal, W->state, m);
+    c->st.kernel_launches++;
+    if ((rc = poll(c))) return rc;
+    if (W->h_state[0]) { converged = true; break; }
+    if (its >= maxits) break;
+    k_scale_dev<<<grid_for(n), 256, 0, c->stream>>>(n, W->V, W->scal + 3, W->state);
+    c->st.kernel_launches++;
+    int j = 0;
+    for (; j < m && its < maxits; j++) {
+      double* vj = W->V + (size_t)j * ld;
+      double* vn = W->V + (size_t)(j + 1) * ld;
+      if ((rc = halo_exchange(c, vj))) return rc;
+      if ((rc = launch_spmv(c, vj, vn, scale, true))) return rc;         // vn = B A vj
+      if ((rc = multidot(c, j + 1, W->V, vn, false))) return rc;    // classical Gram-Schmidt: all dots first
+      k_gs_update<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, j + 1, W->V, ld, vn, W->h, W->partial, W->counter,
+                                                            W->h + 512, W->state);
+      c->st.kernel_launches++;
+      if ((rc = allreduce_sum(c, W->h + 512, 1))) return rc;
+      k_gmres_givens<<<1, 1, 0, c->stream>>>(j, m, W->h, W->h + 512, W->H, W->cs, W->sn, W->g, W->scal, W->state);
+      k_scale_dev<<<grid_for(n), 256, 0, c->stream>>>(n, vn, W->scal + 3, W->state);
+      c->st.kernel_launches += 2;
+      its++;
+      if ((j + 1) % sync_every == 0 || j + 1 == m || its >= maxits) {
+        if ((rc = poll(c))) return rc;
+        if (W->h_state[0]) break;
+      }
+    }
+    // x += V y for the columns completed on the device
+    k_gmres_backsolve<<<1, 1, 0, c->stream>>>(m, W->H, W->g, W->y, W->state);
+    k_update_x<<<grid_for(n), 256, 0, c->stream>>>(n, W->state + 2, W->V, ld, W->y, c->d_u);
+    c->st.kernel_launches += 2;
+    RDC_CUDA(cudaGetLastError());
+    if ((rc = poll(c))) return rc;
+    its = W->h_state[1];
+    if (W->h_state[3]) { c->err = "GMRES breakdown (NaN residual)"; *its_out = its; *res_out = W->h_scal[0]; return RDC_E_DIVERGED; }
+    if (W->h_state[0]) { converged = true; break; }
+    if (its >= maxits) break;
+    RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int), c->stream));  // keep counters, clear done
+  }
+  if ((rc = poll(c))) return rc;
+  *its_out = W->h_state[1];
+  *res_out = W->h_scal[0];
+  c->st.resnorm0 = W->h_scal[5];
+  (void)converged;
+  return 0;
+}
+
+// ---- CG / BiCGStab building blocks: coefficients live in W->scal, computed by one-thread kernels ----
+// y = a*x + b*y with a = sa * A[ia] (A == nullptr -> sa), b likewise
+__global__ void k_axpby_dev(size_t n, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ S, int ia,
+                            double sa, int ib, double sb, const int* __restrict__ done) {
+  if (done && *done) return;
+  const double a = ia >= 0 ? sa * S[ia] : sa, b = ib >= 0 ? sb * S[ib] : sb;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = fma(a, x[i], b * y[i]);
+}
+enum { S_RES = 0, S_TARGET = 1, S_RHO = 8, S_RHO_OLD = 9, S_ALPHA = 10, S_BETA = 11, S_OMEGA = 12, S_TMP = 13 };
+
+// PCG scalar steps
+__global__ void k_cg_alpha(const double* pAp, double* S, int* state) {  // alpha = rho / <p, Ap>
+  if (state[0]) return;
+  S[S_ALPHA] = S[S_RHO] / pAp[0];
+}
+__global__ void k_cg_beta(const double* rz_rr, double* S, int* state) {  // rho_new = <r,z>; res = sqrt(<z,z>) (precond. norm)
+  if (state[0]) return;
+  S[S_RHO_OLD] = S[S_RHO];
+  S[S_RHO] = rz_rr[0];
+  S[S_BETA] = S[S_RHO] / S[S_RHO_OLD];
+  const double res = sqrt(rz_rr[1]);
+  S[S_RES] = res;
+  state[1] += 1;
+  if (!(res == res)) { state[0] = 1; state[3] = 1; }
+  else if (res <= S[S_TARGET]) state[0] = 1;
+}
+
+static int axpby(rdc_ctx* c, size_t n, const double* x, double* y, int ia, double sa, int ib, double sb) {
+  SolverWork* W = c->work;
+  k_axpby_dev<<<grid_for(n), 256, 0, c->stream>>>(n, x, y, W->scal, ia, sa, ib, sb, W->state);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Jacobi-PCG (for the symmetric positive definite cases only; convergence on ||B r||)
+static int pcg(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
+  SolverWork* W = c->work;
+  int rc = ensure_extra_vectors(c);
+  if (rc) return rc;
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  static int sync_every = -1;
+  if (sync_every < 0) { const char* e = getenv("RDC_SYNC_EVERY"); sync_every = e ? atoi(e) : 4; if (sync_every < 1) sync_every = 1; }
+  double *r = W->t1, *z = W->t2, *p = W->t3, *Ap = W->t4;
+  RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
+  k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, scale, W->t0);
+  if ((rc = multidot(c, 0, W->t0, W->t0, true))) return rc;
+  k_set_target<<<1, 1, 0, c->stream>>>(W->h, rtol, W->scal);
+  if ((rc = halo_exchange(c, c->d_u))) return rc;
+  if ((rc = launch_spmv(c, c->d_u, W->t0, nullptr, false))) return rc;
+  k_residual<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, W->t0, nullptr, r);
+  k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, r, scale, z);
+  c->st.kernel_launches += 4;
+  RDC_CUDA(cudaMemcpyAsync(p, z, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  // rho = <r,z>, res = ||z||
+  if ((rc = multidot(c, 1, r, z, true))) return rc;
+  RDC_CUDA(cudaMemcpyAsync(W->scal + S_RHO, W->h, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = poll(c))) return rc;
+  {
+    double hz[2];
+    RDC_CUDA(cudaMemcpy(hz, W->h, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (sqrt(hz[1]) <= W->h_scal[S_TARGET]) { *its_out = 0; *res_out = sqrt(hz[1]); c->st.resnorm0 = W->h_scal[5]; return 0; }
+  }
+  int its = 0;
+  while (its < maxits) {
+    if ((rc = halo_exchange(c, p))) return rc;
+    if ((rc = launch_spmv(c, p, Ap, nullptr, true))) return rc;
+    if ((rc = multidot(c, 1, p, Ap, false))) return rc;
+    k_cg_alpha<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
+    c->st.kernel_launches++;
+    if ((rc = axpby(c, n, p, c->d_u, S_ALPHA, 1.0, -1, 1.0))) return rc;    // x += alpha p
+    if ((rc = axpby(c, n, Ap, r, S_ALPHA, -1.0, -1, 1.0))) return rc;       // r -= alpha Ap
+    k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, r, scale, z);
+    c->st.kernel_launches++;
+    if ((rc = multidot(c, 1, r, z, true))) return rc;                       // <r,z>, <z,z>
+    k_cg_beta<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
+    c->st.kernel_launches++;
+    if ((rc = axpby(c, n, z, p, -1, 1.0, S_BETA, 1.0))) return rc;          // p = z + beta p
+    its++;
+    if (its % sync_every == 0 || its >= maxits) {
+      if ((rc = poll(c))) return rc;
+      if (W->h_state[0]) break;
+    }
+  }
+  if ((rc = poll(c))) return rc;
+  *its_out = W->h_state[1];
+  *res_out = W->h_scal[S_RES];
+  c->st.resnorm0 = W->h_scal[5];
+  if (W->h_state[3]) { c->err = "CG breakdown"; return RDC_E_DIVERGED; }
+  return 0;
+}
+
+// BiCGStab scalar steps (left-preconditioned system B A x = B b)
+__global__ void k_bi_rho(const double* d, double* S, int* state, int first) {  // rho = <r0, r>; beta
+  if (state[0]) return;
+  S[S_RHO_OLD] = S[S_RHO];
+  S[S_RHO] = d[0];
+  S[S_BETA] = first ? 0.0 : (S[S_RHO] / S[S_RHO_OLD]) * (S[S_ALPHA] / S[S_OMEGA]);
+  S[S_TMP] = -S[S_BETA] * S[S_OMEGA];
+}
+__global__ void k_bi_alpha(const double* d, double* S, int* state) {  // alpha = rho / <r0, v>
+  if (state[0]) return;
+  S[S_ALPHA] = S[S_RHO] / d[0];
+}
+__global__ void k_bi_omega(const double* d, double* S, int* state) {  // omega = <t,s>/<t,t>
+  if (state[0]) return;
+  S[S_OMEGA] = d[1] != 0.0 ? d[0] / d[1] : 0.0;
+}
+__global__ void k_bi_res(const double* d, double* S, int* state) {
+  if (state[0]) return;
+  const double res = sqrt(d[0]);
+  S[S_RES] = res;
+  state[1] += 1;
+  if (!(res == res) || S[S_OMEGA] == 0.0) { state[0] = 1; state[3] = (res <= S[S_TARGET]) ? 0 : 1; }
+  else if (res <= S[S_TARGET]) state[0] = 1;
+}
+
+static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
+  SolverWork* W = c->work;
+  int rc = ensure_extra_vectors(c);
+  if (rc) return rc;
+  rc = ensure_gmres(c, 2);  // borrow V for three more vectors
+  if (rc) return rc;
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  static int sync_every = -1;
+  if (sync_every < 0) { const char* e = getenv("RDC_SYNC_EVERY"); sync_every = e ? atoi(e) : 4; if (sync_every < 1) sync_every = 1; }
+  double *r = W->t1, *r0 = W->t2, *p = W->t3, *v = W->t4, *s = W->V, *t = W->V + W->vec_len;
+  RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
+  k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, scale, W->t0);
+  if ((rc = multidot(c, 0, W->t0, W->t0, true))) return rc;
+  k_set_target<<<1, 1, 0, c->stream>>>(W->h, rtol, W->scal);
+  if ((rc = halo_exchange(c, c->d_u))) return rc;
+  if ((rc = launch_spmv(c, c->d_u, W->t0, nullptr, false))) return rc;
+  k_residual<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, W->t0, scale, r);   // r = B(b - A x)
+  c->st.kernel_launches += 3;
+  RDC_CUDA(cudaMemcpyAsync(r0, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  RDC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), c->stream));
+  RDC_CUDA(cudaMemsetAsync(v, 0, n * sizeof(double), c->stream));
+  if ((rc = multidot(c, 0, r, r, true))) return rc;
+  if ((rc = poll(c))) return rc;
+  {
+    double h0;
+    RDC_CUDA(cudaMemcpy(&h0, W->h, sizeof(double), cudaMemcpyDeviceToHost));
+    if (sqrt(h0) <= W->h_scal[S_TARGET]) { *its_out = 0; *res_out = sqrt(h0); c->st.resnorm0 = W->h_scal[5]; return 0; }
+  }
+  int its = 0;
+  while (its < maxits) {
+    if ((rc = multidot(c, 1, r0, r, false))) return rc;
+    k_bi_rho<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state, its == 0);
+    c->st.kernel_launches++;
+    // p = r + beta (p - omega v)  ==  p = beta p + (-beta omega) v + r
+    if ((rc = axpby(c, n, v, p, S_TMP, 1.0, S_BETA, 1.0))) return rc;
+    if ((rc = axpby(c, n, r, p, -1, 1.0, -1, 1.0))) return rc;
+    if ((rc = halo_exchange(c, p))) return rc;
+    if ((rc = launch_spmv(c, p, v, scale, true))) return rc;                       // v = B A p
+    if ((rc = multidot(c, 1, r0, v, false))) return rc;
+    k_bi_alpha<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
+    c->st.kernel_launches++;
+    RDC_CUDA(cudaMemcpyAsync(s, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = axpby(c, n, v, s, S_ALPHA, -1.0, -1, 1.0))) return rc;         // s = r - alpha v
+    if ((rc = halo_exchange(c, s))) return rc;
+    if ((rc = launch_spmv(c, s, t, scale, true))) return rc;                       // t = B A s
+    if ((rc = multidot(c, 1, s, t, true))) return rc;                        // <t,s>, <t,t>
+    k_bi_omega<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
+    c->st.kernel_launches++;
+    if ((rc = axpby(c, n, p, c->d_u, S_ALPHA, 1.0, -1, 1.0))) return rc;     // x += alpha p + omega s
+    if ((rc = axpby(c, n, s, c->d_u, S_OMEGA, 1.0, -1, 1.0))) return rc;
+    RDC_CUDA(cudaMemcpyAsync(r, s, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if ((rc = axpby(c, n, t, r, S_OMEGA, -1.0, -1, 1.0))) return rc;         // r = s - omega t
+    if ((rc = multidot(c, 0, r, r, true))) return rc;
+    k_bi_res<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
+    c->st.kernel_launches++;
+    its++;
+    if (its % sync_every == 0 || its >= maxits) {
+      if ((rc = poll(c))) return rc;
+      if (W->h_state[0]) break;
+    }
+  }
+  if ((rc = poll(c))) return rc;
+  *its_out = W->h_state[1];
+  *res_out = W->h_scal[S_RES];
+  c->st.resnorm0 = W->h_scal[5];
+  if (W->h_state[3]) { c->err = "BiCGStab breakdown"; return RDC_E_DIVERGED; }
+  return 0;
+}
+
+int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int restart, int* its, double* res) {
+  const double* scale = nullptr;
+  if (pc == RDC_PC_JACOBI) {
+    int rc = launch_extract_diag(c);
+    if (rc) return rc;
+    scale = c->d_dinv;
+  } else if (pc != RDC_PC_NONE) {
+    c->err = "preconditioner not implemented on the device path (use RDC_PC_JACOBI or RDC_PC_NONE)";
+    return RDC_E_ARG;
+  }
+  if (restart < 1) restart = 30;
+  SolverWork* W = c->work;
+  W->n_ev_used = 0;
+  int rc;
+  if (ksp == RDC_KSP_GMRES) rc = gmres(c, scale, rtol, maxits, restart, its, res);
+  else if (ksp == RDC_KSP_CG) rc = pcg(c, scale, rtol, maxits, its, res);
+  else if (ksp == RDC_KSP_BICGSTAB) rc = bicgstab(c, scale, rtol, maxits, its, res);
+  else { c->err = "unknown ksp"; return RDC_E_ARG; }
+  // Sum of the event-bracketed SpMV launches of this solve.  Launches issued after convergence return at
+  // once (device-side flag) and add ~0, so the mean over the REAL SpMVs is total / (its * spmv per its).
+  cudaStreamSynchronize(c->stream);
+  double tot = 0.0;
+  for (int k = 0; k < W->n_ev_used; k++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, W->ev[2 * k], W->ev[2 * k + 1]) == cudaSuccess) tot += ms;
+  }
+  c->st.ms_spmv_total = tot;
+  c->st.n_spmv = (*its) * (ksp == RDC_KSP_BICGSTAB ? 2 : 1);
+  return rc;
+}
+
+}  // namespace rdc

