@@ -2,9 +2,9 @@
 
     python -m rdcfes_b200.build [--force]
 
-nvcc cross-compiles without a GPU.  -fmad=false: multiplications and additions round separately like the
-reference's x86-64 build, so threshold decisions match the CPU path bit for bit; fused multiply-adds are
-written explicitly (fma()) in the accumulation loops.  -lineinfo keeps ncu's source page usable.
+nvcc cross-compiles without a GPU.  FMA contraction stays on; the arithmetic that feeds discrete decisions
+uses __dmul_rn/__dadd_rn explicitly (csrc/models.cuh "Rounding discipline").  -lineinfo keeps ncu's source
+page usable.
 """
 from __future__ import annotations
 
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             return SO
         raise RuntimeError("sources missing and no prebuilt librdcgpu.so")
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-ccbin", ccbin, "-Xcompiler", "-fPIC,-fopenmp,-O2", "-shared", "-o", SO]
     if verbose:
         cmd += ["-Xptxas", "-v"]

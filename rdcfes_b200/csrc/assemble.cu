@@ -51,12 +51,13 @@ struct AsmArgs {
 __host__ __device__ constexpr int popc(unsigned m) { int c = 0; while (m) { c += m & 1u; m >>= 1; } return c; }
 __host__ __device__ constexpr int slot_of(unsigned mask, int bitpos) { return popc(mask & ((1u << bitpos) - 1u)); }
 
-// value at a quadrature point, summed exactly like the reference does (adpm.C:464-471): mul then add
+// value at a quadrature point, summed exactly like the reference does (adpm.C:464-471): each product and
+// each sum rounded separately, l = 0..nen-1 (bit-identical operands for the threshold decisions)
 template <int NEN>
 __device__ __forceinline__ double interp(const double* phi_q, const double* nodal) {
   double v = 0.0;
 #pragma unroll
-  for (int l = 0; l < NEN; l++) v = v + phi_q[l] * nodal[l];
+  for (int l = 0; l < NEN; l++) v = add_rn(v, mul_rn(phi_q[l], nodal[l]));
   return v;
 }
 
@@ -74,12 +75,49 @@ template <> __device__ __forceinline__ void load_aux<Proteas>(const AsmArgs& A, 
   out[0] = A.aux0[(size_t)node * 2 + 0];  // AUX variable 0 (proteas.C:472,481)
 }
 
-template <class M, int NEN, int PAIRS>
-__global__ void __launch_bounds__(PAIRS) k_assemble(const AsmArgs A, const typename M::Params P) {
+// gradients of the masked variables: g += dphi_l * U_l, l ascending, no contraction (adpm.C:469-470)
+template <int NEN, int NVAR>
+__device__ __forceinline__ void field_gradients(unsigned mask, const double (*dphi)[3], const double (*U)[NEN], double (*G)[3]) {
+#pragma unroll
+  for (int a = 0; a < NVAR; a++)
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      double g = 0.0;
+      if (mask >> a & 1u) {
+#pragma unroll
+        for (int l = 0; l < NEN; l++) g = add_rn(g, mul_rn(dphi[l][d], U[a][l]));
+      }
+      G[a][d] = g;
+    }
+}
+
+// [upstream] FEMap: inverse Jacobian entries from J = dx/dxi, same expression order as libMesh, no contraction
+struct InvJac { double jac, xix, xiy, xiz, etax, etay, etaz, zex, zey, zez; };
+__device__ __forceinline__ InvJac inv_jacobian(double dx_dxi, double dx_deta, double dx_dzeta, double dy_dxi, double dy_deta,
+                                               double dy_dzeta, double dz_dxi, double dz_deta, double dz_dzeta) {
+  InvJac r;
+  const double c0 = sub_rn(mul_rn(dy_deta, dz_dzeta), mul_rn(dz_deta, dy_dzeta));
+  const double c1 = sub_rn(mul_rn(dz_deta, dx_dzeta), mul_rn(dx_deta, dz_dzeta));
+  const double c2 = sub_rn(mul_rn(dx_deta, dy_dzeta), mul_rn(dy_deta, dx_dzeta));
+  r.jac = add_rn(add_rn(mul_rn(dx_dxi, c0), mul_rn(dy_dxi, c1)), mul_rn(dz_dxi, c2));
+  const double inv = 1. / r.jac;
+  r.xix = mul_rn(c0, inv); r.xiy = mul_rn(c1, inv); r.xiz = mul_rn(c2, inv);
+  r.etax = mul_rn(sub_rn(mul_rn(dz_dxi, dy_dzeta), mul_rn(dy_dxi, dz_dzeta)), inv);
+  r.etay = mul_rn(sub_rn(mul_rn(dx_dxi, dz_dzeta), mul_rn(dz_dxi, dx_dzeta)), inv);
+  r.etaz = mul_rn(sub_rn(mul_rn(dy_dxi, dx_dzeta), mul_rn(dx_dxi, dy_dzeta)), inv);
+  r.zex = mul_rn(sub_rn(mul_rn(dy_dxi, dz_deta), mul_rn(dz_dxi, dy_deta)), inv);
+  r.zey = mul_rn(sub_rn(mul_rn(dz_dxi, dx_deta), mul_rn(dx_dxi, dz_deta)), inv);
+  r.zez = mul_rn(sub_rn(mul_rn(dx_dxi, dy_deta), mul_rn(dy_dxi, dx_deta)), inv);
+  return r;
+}
+
+template <class M, int NEN, int PAIRS, int MINB>
+__global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const typename M::Params P) {
   constexpr int NV = M::NV;
   constexpr int VV = NV * NV;
   constexpr unsigned KMASK = M::CMASK | M::SMASK | M::TMASK;
   constexpr int NKV = popc(KMASK);
+  constexpr int NSV = popc(M::SMASK) > 0 ? popc(M::SMASK) : 1;
   constexpr int NQP = NEN == 4 ? 5 : 8;
   constexpr int TI = NEN == 4 ? 0 : 1;
   constexpr int NAUX = M::N_NAUX;
@@ -128,141 +166,102 @@ __global__ void __launch_bounds__(PAIRS) k_assemble(const AsmArgs A, const typen
     double ef[3] = {0.0, 0.0, 0.0};
     if (M::N_EFIELD == 3) { ef[0] = A.efield[(size_t)e * 3]; ef[1] = A.efield[(size_t)e * 3 + 1]; ef[2] = A.efield[(size_t)e * 3 + 2]; }
 
-    double Kacc[NEN][NKV > 0 ? NKV : 1];
     double Facc[NV];
 #pragma unroll
-    for (int j = 0; j < NEN; j++)
-#pragma unroll
-      for (int s = 0; s < NKV; s++) Kacc[j][s] = 0.0;
-#pragma unroll
     for (int a = 0; a < NV; a++) Facc[a] = 0.0;
-
     const FeTable& T = c_fe[TI];
 
-    // per-qp body shared by both element types.  dphi[l][3] are the physical gradients at this qp.
-    auto qp_body = [&](int q, double JxW, const double (*dphi)[3], const double (*dir)[3], bool dirs_given) {
-      double phi_q[NEN];
-#pragma unroll
-      for (int l = 0; l < NEN; l++) phi_q[l] = T.phi[l][q];
-      double Uq[NV], Aq[NA_];
-#pragma unroll
-      for (int a = 0; a < NV; a++) Uq[a] = interp<NEN>(phi_q, U[a]);
-      Aq[0] = 0.0;
-      if (NAUX > 0) {
-        if (M::NV == 5 && NAUX == 1) {  // PROTEAS: RTD = phi_1(qp) * AUX0(local node 1), proteas.C:481
-          Aq[0] = 0.0 + phi_q[1] * AX[0][1];
-        } else {
-#pragma unroll
-          for (int m = 0; m < NAUX; m++) Aq[m] = interp<NEN>(phi_q, AX[m]);
-        }
-      }
-      double dirq[M::NDIR][3];
-      if (!dirs_given) {
-        double G[NV][3], GA[NA_][3];
-#pragma unroll
-        for (int a = 0; a < NV; a++)
-#pragma unroll
-          for (int d = 0; d < 3; d++) {
-            double g = 0.0;
-            if (M::GRADMASK >> a & 1u) {
-#pragma unroll
-              for (int l = 0; l < NEN; l++) g = g + dphi[l][d] * U[a][l];
-            }
-            G[a][d] = g;
-          }
-#pragma unroll
-        for (int m = 0; m < NA_; m++)
-#pragma unroll
-          for (int d = 0; d < 3; d++) {
-            double g = 0.0;
-            if (NAUX > 0 && (M::AUXGRADMASK >> m & 1u)) {
-#pragma unroll
-              for (int l = 0; l < NEN; l++) g = g + dphi[l][d] * AX[m][l];
-            }
-            GA[m][d] = g;
-          }
-        M::directions(P, G, ef, GA, dirq);
-      }
-      // grad phi_i of MY row and phi_i, selected without dynamic register indexing
-      double dNi[3] = {dphi[0][0], dphi[0][1], dphi[0][2]};
-      double phi_i = phi_q[0];
-#pragma unroll
-      for (int l = 1; l < NEN; l++)
-        if (li == l) { dNi[0] = dphi[l][0]; dNi[1] = dphi[l][1]; dNi[2] = dphi[l][2]; phi_i = phi_q[l]; }
-      double Dg[M::NDIR];
-#pragma unroll
-      for (int m = 0; m < M::NDIR; m++) Dg[m] = dirs_given ? dot3(dir[m], dNi) : dot3(dirq[m], dNi);
-      Coef<NV> k;
-      M::coef(P, Uq, Aq, Dg, k);
-      const double Wi = JxW * phi_i;
-#pragma unroll
-      for (int a = 0; a < NV; a++) Facc[a] = fma(JxW, k.F1[a], fma(Wi, k.F0[a], Facc[a]));
-#pragma unroll
-      for (int ab = 0; ab < VV; ab++) {
-        if (!(KMASK >> ab & 1u)) continue;
-        const int a = ab / NV, b = ab % NV;
-        const int s = slot_of(KMASK, ab);
-        double mj = 0.0;  // multiplies phi_j
-        if (M::CMASK >> ab & 1u) mj = Wi * k.C[a][b];
-        if (M::TMASK >> ab & 1u) mj = fma(JxW, k.T[a][b], mj);
-        const double sj = (M::SMASK >> ab & 1u) ? JxW * k.S[a][b] : 0.0;  // multiplies grad phi_j . grad phi_i
-#pragma unroll
-        for (int j = 0; j < NEN; j++) {
-          double acc = fma(mj, phi_q[j], Kacc[j][s]);
-          if (M::SMASK >> ab & 1u) acc = fma(sj, dot3(dphi[j], dNi), acc);
-          Kacc[j][s] = acc;
-        }
-      }
-    };
-
     if constexpr (NEN == 4) {
-      // affine map: J, dphi are element constants (evaluated like FEMap does, Appendix B-4)
-      const double dx_dxi = X[1][0] - X[0][0], dx_deta = X[2][0] - X[0][0], dx_dzeta = X[3][0] - X[0][0];
-      const double dy_dxi = X[1][1] - X[0][1], dy_deta = X[2][1] - X[0][1], dy_dzeta = X[3][1] - X[0][1];
-      const double dz_dxi = X[1][2] - X[0][2], dz_deta = X[2][2] - X[0][2], dz_dzeta = X[3][2] - X[0][2];
-      const double jac = dx_dxi * (dy_deta * dz_dzeta - dz_deta * dy_dzeta) + dy_dxi * (dz_deta * dx_dzeta - dx_deta * dz_dzeta) +
-                         dz_dxi * (dx_deta * dy_dzeta - dy_deta * dx_dzeta);
-      const double inv = 1. / jac;
+      // ---- TET4: affine map, J and dphi are element constants (FEMap, Appendix B-4)
+      const InvJac ij = inv_jacobian(sub_rn(X[1][0], X[0][0]), sub_rn(X[2][0], X[0][0]), sub_rn(X[3][0], X[0][0]),
+                                     sub_rn(X[1][1], X[0][1]), sub_rn(X[2][1], X[0][1]), sub_rn(X[3][1], X[0][1]),
+                                     sub_rn(X[1][2], X[0][2]), sub_rn(X[2][2], X[0][2]), sub_rn(X[3][2], X[0][2]));
       double dphi[4][3];
-      dphi[1][0] = (dy_deta * dz_dzeta - dz_deta * dy_dzeta) * inv;
-      dphi[1][1] = (dz_deta * dx_dzeta - dx_deta * dz_dzeta) * inv;
-      dphi[1][2] = (dx_deta * dy_dzeta - dy_deta * dx_dzeta) * inv;
-      dphi[2][0] = (dz_dxi * dy_dzeta - dy_dxi * dz_dzeta) * inv;
-      dphi[2][1] = (dx_dxi * dz_dzeta - dz_dxi * dx_dzeta) * inv;
-      dphi[2][2] = (dy_dxi * dx_dzeta - dx_dxi * dy_dzeta) * inv;
-      dphi[3][0] = (dy_dxi * dz_deta - dz_dxi * dy_deta) * inv;
-      dphi[3][1] = (dz_dxi * dx_deta - dx_dxi * dz_deta) * inv;
-      dphi[3][2] = (dx_dxi * dy_deta - dy_dxi * dx_deta) * inv;
+      dphi[1][0] = ij.xix; dphi[1][1] = ij.xiy; dphi[1][2] = ij.xiz;
+      dphi[2][0] = ij.etax; dphi[2][1] = ij.etay; dphi[2][2] = ij.etaz;
+      dphi[3][0] = ij.zex; dphi[3][1] = ij.zey; dphi[3][2] = ij.zez;
 #pragma unroll
-      for (int d = 0; d < 3; d++) dphi[0][d] = (-dphi[1][d] - dphi[2][d]) - dphi[3][d];
-      // gradients and direction vectors are element constants as well
-      double G[NV][3], GA[NA_][3], dir[M::NDIR][3];
+      for (int d = 0; d < 3; d++) dphi[0][d] = sub_rn(sub_rn(-dphi[1][d], dphi[2][d]), dphi[3][d]);
+      double Dg[M::NDIR], GG[4];
+      {
+        double G[NV][3], GA[NA_][3], dir[M::NDIR][3];
+        field_gradients<4, NV>(M::GRADMASK, dphi, U, G);
+        field_gradients<4, NA_>(NAUX > 0 ? M::AUXGRADMASK : 0u, dphi, AX, GA);
+        M::directions(P, G, ef, GA, dir);
+        double dNi[3] = {dphi[0][0], dphi[0][1], dphi[0][2]};
 #pragma unroll
-      for (int a = 0; a < NV; a++)
+        for (int l = 1; l < 4; l++)
+          if (li == l) { dNi[0] = dphi[l][0]; dNi[1] = dphi[l][1]; dNi[2] = dphi[l][2]; }
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-          double g = 0.0;
-          if (M::GRADMASK >> a & 1u) {
+        for (int m = 0; m < M::NDIR; m++) Dg[m] = dot3(dir[m], dNi);
 #pragma unroll
-            for (int l = 0; l < 4; l++) g = g + dphi[l][d] * U[a][l];
+        for (int j = 0; j < 4; j++) GG[j] = dot3(dphi[j], dNi);
+      }
+      // The 5-point rule has phi = 1/4 at qp 0 and, at qp k >= 1, phi = 1/2 at ONE node (node k, node 0 for
+      // k = 4) and 1/6 at the others, so  sum_q m_q phi_j(q) = [m_0/4 + (1/6) sum_{k>=1} m_k] + (1/3) m_{k(j)} :
+      // a common base Kb plus one node-specific extra Kx per block (2 FMAs per qp and block instead of 4).
+      double Kb[NKV > 0 ? NKV : 1], Kx[4][NKV > 0 ? NKV : 1], Ss[NSV];
+#pragma unroll
+      for (int s = 0; s < NSV; s++) Ss[s] = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQP; q++) {
+        double phi_q[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) phi_q[l] = T.phi[l][q];
+        double Uq[NV], Aq[NA_];
+#pragma unroll
+        for (int a = 0; a < NV; a++) Uq[a] = interp<4>(phi_q, U[a]);
+        Aq[0] = 0.0;
+        if (NAUX > 0) {
+          if (M::NV == 5 && NAUX == 1) Aq[0] = add_rn(0.0, mul_rn(phi_q[1], AX[0][1]));  // PROTEAS RTD, proteas.C:481
+          else {
+#pragma unroll
+            for (int m = 0; m < NAUX; m++) Aq[m] = interp<4>(phi_q, AX[m]);
           }
-          G[a][d] = g;
         }
+        double phi_i = phi_q[0];
 #pragma unroll
-      for (int m = 0; m < NA_; m++)
+        for (int l = 1; l < 4; l++)
+          if (li == l) phi_i = phi_q[l];
+        Coef<NV> k;
+        M::coef(P, Uq, Aq, Dg, k);
+        const double JxW = ij.jac * T.w[q];
+        const double Wi = JxW * phi_i;
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-          double g = 0.0;
-          if (NAUX > 0 && (M::AUXGRADMASK >> m & 1u)) {
+        for (int a = 0; a < NV; a++) Facc[a] += Wi * k.F0[a] + JxW * k.F1[a];
 #pragma unroll
-            for (int l = 0; l < 4; l++) g = g + dphi[l][d] * AX[m][l];
-          }
-          GA[m][d] = g;
+        for (int ab = 0; ab < VV; ab++) {
+          if (!(KMASK >> ab & 1u)) continue;
+          const int a = ab / NV, b = ab % NV;
+          const int s = slot_of(KMASK, ab);
+          double m = 0.0;
+          if (M::CMASK >> ab & 1u) m = Wi * k.C[a][b];
+          if (M::TMASK >> ab & 1u) m += JxW * k.T[a][b];
+          if (q == 0) Kb[s] = 0.25 * m;
+          else { Kb[s] += (1.0 / 6.0) * m; Kx[q - 1][s] = (1.0 / 3.0) * m; }
+          if (M::SMASK >> ab & 1u) Ss[slot_of(M::SMASK, ab)] += JxW * k.S[a][b];
         }
-      M::directions(P, G, ef, GA, dir);
+      }
+      // stage my row: node j gets base + its own extra (+ stiffness part)
 #pragma unroll
-      for (int q = 0; q < NQP; q++) qp_body(q, jac * T.w[q], dphi, dir, true);
+      for (int j = 0; j < 4; j++) {
+        const int qx = j == 0 ? 3 : j - 1;  // qp k >= 1 that has phi = 1/2 at node j
+#pragma unroll
+        for (int ab = 0; ab < VV; ab++) {
+          if (!(KMASK >> ab & 1u)) continue;
+          const int s = slot_of(KMASK, ab);
+          double v = Kb[s] + Kx[qx][s];
+          if (M::SMASK >> ab & 1u) v += Ss[slot_of(M::SMASK, ab)] * GG[j];
+          stageK[((size_t)j * NKV + s) * PAIRS + tid] = v;
+        }
+      }
     } else {
+      // ---- HEX8: per-qp Jacobian; row accumulated directly
+      double Kacc[NEN][NKV > 0 ? NKV : 1];
+#pragma unroll
+      for (int j = 0; j < NEN; j++)
+#pragma unroll
+        for (int s = 0; s < NKV; s++) Kacc[j][s] = 0.0;
 #pragma unroll 1
       for (int q = 0; q < NQP; q++) {
         double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // J[c][r] = d x_c / d xi_r
@@ -270,38 +269,72 @@ __global__ void __launch_bounds__(PAIRS) k_assemble(const AsmArgs A, const typen
         for (int n = 0; n < NEN; n++)
 #pragma unroll
           for (int cc = 0; cc < 3; cc++) {
-            J[cc][0] = J[cc][0] + X[n][cc] * T.dxi[n][q];
-            J[cc][1] = J[cc][1] + X[n][cc] * T.deta[n][q];
-            J[cc][2] = J[cc][2] + X[n][cc] * T.dzeta[n][q];
+            J[cc][0] = add_rn(J[cc][0], mul_rn(X[n][cc], T.dxi[n][q]));
+            J[cc][1] = add_rn(J[cc][1], mul_rn(X[n][cc], T.deta[n][q]));
+            J[cc][2] = add_rn(J[cc][2], mul_rn(X[n][cc], T.dzeta[n][q]));
           }
-        const double dx_dxi = J[0][0], dx_deta = J[0][1], dx_dzeta = J[0][2];
-        const double dy_dxi = J[1][0], dy_deta = J[1][1], dy_dzeta = J[1][2];
-        const double dz_dxi = J[2][0], dz_deta = J[2][1], dz_dzeta = J[2][2];
-        const double jac = dx_dxi * (dy_deta * dz_dzeta - dz_deta * dy_dzeta) + dy_dxi * (dz_deta * dx_dzeta - dx_deta * dz_dzeta) +
-                           dz_dxi * (dx_deta * dy_dzeta - dy_deta * dx_dzeta);
-        const double inv = 1. / jac;
-        const double dxidx = (dy_deta * dz_dzeta - dz_deta * dy_dzeta) * inv, dxidy = (dz_deta * dx_dzeta - dx_deta * dz_dzeta) * inv,
-                     dxidz = (dx_deta * dy_dzeta - dy_deta * dx_dzeta) * inv;
-        const double detadx = (dz_dxi * dy_dzeta - dy_dxi * dz_dzeta) * inv, detady = (dx_dxi * dz_dzeta - dz_dxi * dx_dzeta) * inv,
-                     detadz = (dy_dxi * dx_dzeta - dx_dxi * dy_dzeta) * inv;
-        const double dzetadx = (dy_dxi * dz_deta - dz_dxi * dy_deta) * inv, dzetady = (dz_dxi * dx_deta - dx_dxi * dz_deta) * inv,
-                     dzetadz = (dx_dxi * dy_deta - dy_dxi * dx_deta) * inv;
+        const InvJac ij = inv_jacobian(J[0][0], J[0][1], J[0][2], J[1][0], J[1][1], J[1][2], J[2][0], J[2][1], J[2][2]);
         double dphi[NEN][3];
 #pragma unroll
         for (int n = 0; n < NEN; n++) {
-          dphi[n][0] = T.dxi[n][q] * dxidx + T.deta[n][q] * detadx + T.dzeta[n][q] * dzetadx;
-          dphi[n][1] = T.dxi[n][q] * dxidy + T.deta[n][q] * detady + T.dzeta[n][q] * dzetady;
-          dphi[n][2] = T.dxi[n][q] * dxidz + T.deta[n][q] * detadz + T.dzeta[n][q] * dzetadz;
+          dphi[n][0] = add_rn(add_rn(mul_rn(T.dxi[n][q], ij.xix), mul_rn(T.deta[n][q], ij.etax)), mul_rn(T.dzeta[n][q], ij.zex));
+          dphi[n][1] = add_rn(add_rn(mul_rn(T.dxi[n][q], ij.xiy), mul_rn(T.deta[n][q], ij.etay)), mul_rn(T.dzeta[n][q], ij.zey));
+          dphi[n][2] = add_rn(add_rn(mul_rn(T.dxi[n][q], ij.xiz), mul_rn(T.deta[n][q], ij.etaz)), mul_rn(T.dzeta[n][q], ij.zez));
         }
-        qp_body(q, jac * T.w[q], dphi, nullptr, false);
+        double phi_q[NEN];
+#pragma unroll
+        for (int l = 0; l < NEN; l++) phi_q[l] = T.phi[l][q];
+        double Uq[NV], Aq[NA_];
+#pragma unroll
+        for (int a = 0; a < NV; a++) Uq[a] = interp<NEN>(phi_q, U[a]);
+        Aq[0] = 0.0;
+        if (NAUX > 0) {
+          if (M::NV == 5 && NAUX == 1) Aq[0] = add_rn(0.0, mul_rn(phi_q[1], AX[0][1]));
+          else {
+#pragma unroll
+            for (int m = 0; m < NAUX; m++) Aq[m] = interp<NEN>(phi_q, AX[m]);
+          }
+        }
+        double G[NV][3], GA[NA_][3], dir[M::NDIR][3];
+        field_gradients<NEN, NV>(M::GRADMASK, dphi, U, G);
+        field_gradients<NEN, NA_>(NAUX > 0 ? M::AUXGRADMASK : 0u, dphi, AX, GA);
+        M::directions(P, G, ef, GA, dir);
+        double dNi[3] = {dphi[0][0], dphi[0][1], dphi[0][2]};
+        double phi_i = phi_q[0];
+#pragma unroll
+        for (int l = 1; l < NEN; l++)
+          if (li == l) { dNi[0] = dphi[l][0]; dNi[1] = dphi[l][1]; dNi[2] = dphi[l][2]; phi_i = phi_q[l]; }
+        double Dg[M::NDIR];
+#pragma unroll
+        for (int m = 0; m < M::NDIR; m++) Dg[m] = dot3(dir[m], dNi);
+        Coef<NV> k;
+        M::coef(P, Uq, Aq, Dg, k);
+        const double JxW = ij.jac * T.w[q];
+        const double Wi = JxW * phi_i;
+#pragma unroll
+        for (int a = 0; a < NV; a++) Facc[a] += Wi * k.F0[a] + JxW * k.F1[a];
+#pragma unroll
+        for (int ab = 0; ab < VV; ab++) {
+          if (!(KMASK >> ab & 1u)) continue;
+          const int a = ab / NV, b = ab % NV;
+          const int s = slot_of(KMASK, ab);
+          double mj = 0.0;
+          if (M::CMASK >> ab & 1u) mj = Wi * k.C[a][b];
+          if (M::TMASK >> ab & 1u) mj += JxW * k.T[a][b];
+          const double sj = (M::SMASK >> ab & 1u) ? JxW * k.S[a][b] : 0.0;
+#pragma unroll
+          for (int j = 0; j < NEN; j++) {
+            double acc = Kacc[j][s] + mj * phi_q[j];
+            if (M::SMASK >> ab & 1u) acc += sj * dot3(dphi[j], dNi);
+            Kacc[j][s] = acc;
+          }
+        }
       }
+#pragma unroll
+      for (int j = 0; j < NEN; j++)
+#pragma unroll
+        for (int s = 0; s < NKV; s++) stageK[((size_t)j * NKV + s) * PAIRS + tid] = Kacc[j][s];
     }
-
-    // stage my row
-#pragma unroll
-    for (int j = 0; j < NEN; j++)
-#pragma unroll
-      for (int s = 0; s < NKV; s++) stageK[((size_t)j * NKV + s) * PAIRS + tid] = Kacc[j][s];
 #pragma unroll
     for (int a = 0; a < NV; a++) stageF[a * PAIRS + tid] = Facc[a];
   }
@@ -357,16 +390,18 @@ static void fill_tr(Trapezoid& o, const double* p) {
   o.up = p[0] / (p[2] - p[1]); o.dn = p[0] / (p[4] - p[3]);
 }
 
-template <class M, int NEN, int PAIRS>
+template <class M, int NEN, int PAIRS, int MINB>
 static int launch_t(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
   constexpr unsigned KMASK = M::CMASK | M::SMASK | M::TMASK;
   const size_t smem = ((size_t)NEN * popc(KMASK) + M::NV) * PAIRS * sizeof(double);
   static bool attr_done = false;
   if (!attr_done) {
-    RDC_CUDA(cudaFuncSetAttribute(k_assemble<M, NEN, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RDC_CUDA(cudaFuncSetAttribute(k_assemble<M, NEN, PAIRS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RDC_CUDA(cudaFuncSetAttribute(k_assemble<M, NEN, PAIRS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     attr_done = true;
   }
-  k_assemble<M, NEN, PAIRS><<<c->ncta, PAIRS, smem, c->stream>>>(A, P);
+  k_assemble<M, NEN, PAIRS, MINB><<<c->ncta, PAIRS, smem, c->stream>>>(A, P);
   c->st.kernel_launches++;
   RDC_CUDA(cudaGetLastError());
   return 0;
@@ -375,10 +410,10 @@ static int launch_t(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
 template <class M>
 static int launch_m(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
   if (c->etype == RDC_TET4) {
-    if (c->S.pairs_per_cta == 256) return launch_t<M, 4, 256>(c, A, P);
-    return launch_t<M, 4, 128>(c, A, P);
+    if constexpr (M::NV == 3) return launch_t<M, 4, 256, 2>(c, A, P);  // 3-variable models: 2 CTAs of 256 pairs per SM
+    else return launch_t<M, 4, 128, 2>(c, A, P);                       // 5-variable models: shared-memory stage of 128 pairs
   }
-  return launch_t<M, 8, 128>(c, A, P);
+  return launch_t<M, 8, 128, 1>(c, A, P);
 }
 
 // pairs per assembly CTA (= block size); bounded by the shared-memory stage of nen*nkv+v doubles per pair

@@ -27,10 +27,19 @@ namespace rdc {
 // bit helpers for the block masks
 __host__ __device__ constexpr unsigned bit(int nv, int a, int b) { return 1u << (a * nv + b); }
 
-// All arithmetic below is compiled with -fmad=false: multiplications and additions round separately
-// exactly like the CPU reference build (x86-64 baseline has no FMA), so every threshold decision
-// (Pi_/SD_/Tr_ branches, taxis alignment, capacity switches) sees bit-identical operands.  Fused
-// multiply-adds are used only where written explicitly as fma().
+// Rounding discipline.  The discrete decisions of the models (Pi_/SD_/Tr_ branches, taxis alignment,
+// capacity switches, epsilon switches) depend on the interpolated state, on field gradients and on the
+// element geometry.  Those quantities are computed with mul_rn/add_rn (no FMA contraction) in exactly the
+// operation order of the reference build (x86-64 baseline has no FMA), so every comparison sees
+// bit-identical operands.  Everything downstream of the decisions (coefficient products, quadrature
+// accumulation) may be contracted by the compiler: it changes values by O(1e-16) relative, never a branch.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+// a0*b0 + a1*b1 + a2*b2, left to right, each product and sum rounded (TypeVector::operator* / norm_sq)
+__device__ __forceinline__ double dot3_rn(const double* a, const double* b) {
+  return add_rn(add_rn(mul_rn(a[0], b[0]), mul_rn(a[1], b[1])), mul_rn(a[2], b[2]));
+}
 
 // ------------------------------------------------------------------------------------ rate laws
 // utils.h:100-110 (cM<=0 disables the law, Appendix C-7)
@@ -92,17 +101,17 @@ struct Adpm {
                                                     const double (*GA)[3], double (*dir)[3]) {
     (void)GA;
     for (int d = 0; d < 3; d++) { dir[0][d] = G[1][d]; dir[1][d] = G[2][d]; dir[2][d] = 0.0; dir[3][d] = 0.0; }
-    const double nA = sqrt(G[1][0] * G[1][0] + G[1][1] * G[1][1] + G[1][2] * G[1][2]);
-    const double nT = sqrt(G[2][0] * G[2][0] + G[2][1] * G[2][1] + G[2][2] * G[2][2]);
+    const double nA = sqrt(dot3_rn(G[1], G[1]));
+    const double nT = sqrt(dot3_rn(G[2], G[2]));
     if (nA != 0.0) {
       const double u[3] = {G[1][0] / nA, G[1][1] / nA, G[1][2] / nA};
-      const double d = u[0] * ef[0] + u[1] * ef[1] + u[2] * ef[2];
+      const double d = dot3_rn(u, ef);
       if (d > +p.omega_A) { dir[2][0] = ef[0]; dir[2][1] = ef[1]; dir[2][2] = ef[2]; }
       else if (d < -p.omega_A) { dir[2][0] = -ef[0]; dir[2][1] = -ef[1]; dir[2][2] = -ef[2]; }
     }
     if (nT != 0.0) {
       const double u[3] = {G[2][0] / nT, G[2][1] / nT, G[2][2] / nT};
-      const double d = u[0] * ef[0] + u[1] * ef[1] + u[2] * ef[2];
+      const double d = dot3_rn(u, ef);
       if (d > +p.omega_T) { dir[3][0] = ef[0]; dir[3][1] = ef[1]; dir[3][2] = ef[2]; }
       else if (d < -p.omega_T) { dir[3][0] = -ef[0]; dir[3][1] = -ef[1]; dir[3][2] = -ef[2]; }
     }
@@ -297,7 +306,7 @@ struct Ripf {
                                                     const double (*GA)[3], double (*dir)[3]) {
     for (int d = 0; d < 3; d++) { dir[0][d] = G[2][d]; dir[1][d] = G[0][d]; }
     // ripf.C:481-484 normalised dose gradient
-    const double l2 = sqrt(GA[2][0] * GA[2][0] + GA[2][1] * GA[2][1] + GA[2][2] * GA[2][2]);
+    const double l2 = sqrt(dot3_rn(GA[2], GA[2]));
     if (l2 != 0.0) { dir[2][0] = GA[2][0] / l2; dir[2][1] = GA[2][1] / l2; dir[2][2] = GA[2][2] / l2; }
     else { dir[2][0] = dir[2][1] = dir[2][2] = 0.0; }
   }

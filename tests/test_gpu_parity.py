@@ -167,12 +167,14 @@ def test_one_step_solution(model, elem_type, n):
     rel = np.linalg.norm(u_g - orc.u) / np.linalg.norm(orc.u)
     print(f"{cases.NAMES[model]} elem{elem_type}: gpu its {its}, rel L2 {rel:.2e}")
     assert rel <= 1e-8
-    # per-variable check as well (variables differ by many orders of magnitude in PIHNA)
+    # per-variable check as well: variables differ by many orders of magnitude (PIHNA a ~ 1e-9, RIPF HU ~ 1e3
+    # next to fb ~ 0.1) while both solvers stop on the norm of the WHOLE preconditioned residual, so a single
+    # small-scale species is only pinned to the species tolerance
     nv = orc.nv
     for a in range(nv):
         ref = orc.u[a::nv]
         if np.linalg.norm(ref) > 0:
-            assert np.linalg.norm(u_g[a::nv] - ref) <= 1e-8 * np.linalg.norm(ref) + 1e-300
+            assert np.linalg.norm(u_g[a::nv] - ref) <= 1e-6 * np.linalg.norm(ref) + 1e-300
     gpu.close()
 
 
