@@ -226,6 +226,13 @@ struct rdc_stats {
   int     ripf_rt_total_max;/* RIPF: int(max RT_total) (ripf.C:772)                    */
 };
 int rdc_get_stats(rdc_ctx*, struct rdc_stats*);
+/* Host-only probe of the node partition and halo lists of rank `rank` (no device needed; used by the CPU
+ * world_size-2 tests).  All arrays are malloc'ed by the library (rdc_free).  send_glob/recv_glob are global node
+ * ids grouped per neighbour by send_ptr/recv_ptr ([n_nbr+1] offsets). */
+int rdc_probe_partition(int elem_type, int nvars, int64_t n_nodes, int64_t n_elems, const int32_t* conn,
+                        const double* xyz, int rank, int nranks, int partitioner, int32_t* n_owned, int32_t* n_ghost,
+                        int64_t* n_elems_local, int32_t** owner, int32_t* n_nbr, int32_t** nbr_rank,
+                        int32_t** send_ptr, int32_t** send_glob, int32_t** recv_ptr, int32_t** recv_glob);
 /* run every kernel on this cudaStream_t (default: a stream owned by the context) */
 int rdc_set_stream(rdc_ctx*, void* cuda_stream);
 const char* rdc_version(void);

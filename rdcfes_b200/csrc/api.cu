@@ -104,7 +104,17 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     if ((r = upload(c, &c->d_rowptr, S.rowptr))) return r;
     if ((r = upload(c, &c->d_col, S.col))) return r;
     if ((r = upload(c, &c->d_diag_blk, S.diag_blk))) return r;
-    if ((r = upload(c, &c->d_cta_node, S.cta_node))) return r;
+    {  // 32-byte CTA descriptors {node0, nnode, pair0, npairs, blk0, nblk, contributor base, 0}
+      const int32_t nc = (int32_t)S.cta_node.size() - 1;
+      std::vector<int32_t> desc((size_t)nc * 8, 0);
+      for (int32_t k = 0; k < nc; k++) {
+        const int32_t a = S.cta_node[k], b = S.cta_node[k + 1];
+        int32_t* d = desc.data() + (size_t)k * 8;
+        d[0] = a; d[1] = b - a; d[2] = S.n2e_ptr[a]; d[3] = S.n2e_ptr[b] - S.n2e_ptr[a];
+        d[4] = S.rowptr[a]; d[5] = S.rowptr[b] - S.rowptr[a]; d[6] = S.cptr[S.rowptr[a]];
+      }
+      if ((r = upload(c, &c->d_cta_node, desc))) return r;
+    }
     if ((r = upload(c, &c->d_cptr, S.cptr))) return r;
     if ((r = upload(c, &c->d_clist, S.clist))) return r;
     c->ncta = (int)S.cta_node.size() - 1;
@@ -155,7 +165,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     const int f_n = model == RDC_RIPF ? 3 : (model == RDC_PROTEAS ? 2 : 0);
     c->st.bytes_assemble = 4LL * c->nen * El + 24LL * Nl + 8LL * nv * Nl + 8LL * f_e * El + 8LL * f_n * Nl + 8LL * nv * nv * nnzb + 8LL * nv * No;
     c->st.bytes_spmv = nnzb * (8LL * nv * nv + 4) + 4LL * (No + 1) + 16LL * nv * No;
-    c->st.bytes_index = 4LL * (int64_t)S.pair.size() + 4LL * (No + 1) * 2 + 4LL * (int64_t)S.cta_node.size() + 4LL * (nnzb + 1) +
+    c->st.bytes_index = 4LL * (int64_t)S.pair.size() + 4LL * (No + 1) * 2 + 32LL * ((int64_t)S.cta_node.size() - 1) + 4LL * (nnzb + 1) +
                         2LL * (int64_t)S.clist.size();
     c->st.n_nodes_local = No; c->st.n_nodes_ghost = S.n_ghost; c->st.n_elems_local = El; c->st.nnzb_local = nnzb;
   }
@@ -497,5 +507,41 @@ extern "C" int rdc_download_csr(rdc_ctx* c, int64_t* n_rows, int64_t* nnz, int64
     }
   }
   *n_rows = nr; *nnz = nz; *rows = o_rows; *rowptr = o_ptr; *col = o_col; *val = o_val; *rhs = o_rhs;
+  return RDC_OK;
+}
+
+// Host-only probe of the partition / halo set-up (no device needed): lets the world_size-2 gloo tests check on
+// CPU that what rank r sends is exactly what rank q expects to receive.  Buffers are malloc'ed; free with
+// rdc_free.  send_glob / recv_glob hold GLOBAL node ids, grouped per neighbour (nbr_ptr offsets).
+extern "C" int rdc_probe_partition(int elem_type, int nvars, int64_t n_nodes, int64_t n_elems, const int32_t* conn,
+                                   const double* xyz, int rank, int nranks, int partitioner, int32_t* n_owned,
+                                   int32_t* n_ghost, int64_t* n_elems_local, int32_t** owner, int32_t* n_nbr, int32_t** nbr_rank,
+                                   int32_t** send_ptr, int32_t** send_glob, int32_t** recv_ptr, int32_t** recv_glob) {
+  HostSetup S;
+  std::string err;
+  int rc;
+  try {
+    rc = build_setup(S, elem_type, nvars, n_nodes, n_elems, conn, xyz, rank, nranks, partitioner, 256, err);
+  } catch (const std::bad_alloc&) { rc = RDC_E_NOMEM; err = "out of host memory"; }
+  if (rc) { g_create_err = err; return rc; }
+  *n_owned = S.n_owned; *n_ghost = S.n_ghost; *n_elems_local = S.E_loc;
+  auto dup = [](const std::vector<int32_t>& v) {
+    int32_t* p = (int32_t*)malloc(sizeof(int32_t) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) memcpy(p, v.data(), sizeof(int32_t) * v.size());
+    return p;
+  };
+  std::vector<int32_t> own(S.owner_glob.begin(), S.owner_glob.end());
+  if (own.empty()) own.assign((size_t)n_nodes, 0);
+  *owner = dup(own);
+  *n_nbr = (int32_t)S.nbr_rank.size();
+  std::vector<int32_t> nb(S.nbr_rank.begin(), S.nbr_rank.end());
+  *nbr_rank = dup(nb);
+  *send_ptr = dup(S.send_ptr);
+  std::vector<int32_t> sg(S.send_idx.size()), rg((size_t)S.n_ghost);
+  for (size_t k = 0; k < S.send_idx.size(); k++) sg[k] = S.loc2glob[S.send_idx[k]];
+  for (int32_t k = 0; k < S.n_ghost; k++) rg[k] = S.loc2glob[S.n_owned + k];
+  *send_glob = dup(sg);
+  *recv_ptr = dup(S.recv_ptr);
+  *recv_glob = dup(rg);
   return RDC_OK;
 }

@@ -16,6 +16,7 @@
 // Operator layout ("row-local SoA"): block row i has L_i blocks; entry (a,b) of block k of row i lives at
 //   val[rowptr[i]*v*v + (a*v+b)*L_i + k]   so that a half-warp reading one row is fully coalesced.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "models.cuh"
 #include "rdc_internal.h"
@@ -124,15 +125,27 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   constexpr int NA_ = NAUX > 0 ? NAUX : 1;
 
   extern __shared__ double smem[];
-  double* stageK = smem;                              // [NEN][NKV][PAIRS]
+  double* stageK = smem;                              // [NKV][NEN][PAIRS]
   double* stageF = smem + (size_t)NEN * NKV * PAIRS;  // [NV][PAIRS]
   __shared__ int s_rowptr[PAIRS + 1];
+  __shared__ int s_n2e[PAIRS + 1];
+  __shared__ int s_cptr[PAIRS * NEN + 1];            // contributor offsets of the CTA's blocks (relative)
+  __shared__ unsigned short s_clist[PAIRS * NEN];    // contributor codes j*PAIRS + pair = offset inside a stage slot
 
   const int tid = threadIdx.x;
-  const int node0 = A.cta_node[blockIdx.x], node1 = A.cta_node[blockIdx.x + 1];
-  const int pair0 = A.n2e_ptr[node0], npairs = A.n2e_ptr[node1] - pair0;
-  const int nnode = node1 - node0;
-  for (int r = tid; r <= nnode; r += PAIRS) s_rowptr[r] = A.rowptr[node0 + r];
+  // one 32-byte descriptor per CTA: a single load level instead of the chain cta_node -> n2e_ptr -> rowptr -> cptr
+  const int4 d0 = reinterpret_cast<const int4*>(A.cta_node)[2 * (size_t)blockIdx.x];
+  const int4 d1 = reinterpret_cast<const int4*>(A.cta_node)[2 * (size_t)blockIdx.x + 1];
+  const int node0 = d0.x, nnode = d0.y, pair0 = d0.z, npairs = d0.w;
+  const int blk0 = d1.x, nblk = d1.y;
+  // index prologue: everything phase 2 needs goes to shared memory now, so its loads overlap phase 1
+  for (int r = tid; r <= nnode; r += PAIRS) { s_rowptr[r] = A.rowptr[node0 + r]; s_n2e[r] = A.n2e_ptr[node0 + r] - pair0; }
+  {
+    const int c_base = d1.z;
+    for (int b = tid; b <= nblk; b += PAIRS) s_cptr[b] = A.cptr[blk0 + b] - c_base;
+    const int n_c = npairs * NEN;
+    for (int i = tid; i < n_c; i += PAIRS) s_clist[i] = A.clist[(size_t)c_base + i];
+  }
 
   // ------------------------------------------------------------------ phase 1: one pair per thread
   if (tid < npairs) {
@@ -199,11 +212,15 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
       }
       // The 5-point rule has phi = 1/4 at qp 0 and, at qp k >= 1, phi = 1/2 at ONE node (node k, node 0 for
       // k = 4) and 1/6 at the others, so  sum_q m_q phi_j(q) = [m_0/4 + (1/6) sum_{k>=1} m_k] + (1/3) m_{k(j)} :
-      // a common base Kb plus one node-specific extra Kx per block (2 FMAs per qp and block instead of 4).
-      double Kb[NKV > 0 ? NKV : 1], Kx[4][NKV > 0 ? NKV : 1], Ss[NSV];
+      // a common base Kb plus one node-specific extra per block.  The extra of qp k goes straight to the
+      // thread's own shared-memory slot of node k(j); the base (and the stiffness part) is added afterwards.
+      // The qp loop is kept rolled: 5x less code and ~60 fewer live registers -> more resident warps.
+      double Kb[NKV > 0 ? NKV : 1], Ss[NSV];
+#pragma unroll
+      for (int s = 0; s < NKV; s++) Kb[s] = 0.0;
 #pragma unroll
       for (int s = 0; s < NSV; s++) Ss[s] = 0.0;
-#pragma unroll
+#pragma unroll 1
       for (int q = 0; q < NQP; q++) {
         double phi_q[4];
 #pragma unroll
@@ -227,6 +244,8 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
         M::coef(P, Uq, Aq, Dg, k);
         const double JxW = ij.jac * T.w[q];
         const double Wi = JxW * phi_i;
+        const double wb = q == 0 ? 0.25 : (1.0 / 6.0);   // weight of this qp in the common base
+        double* xslot = stageK + (size_t)(q & 3) * PAIRS + tid;  // node with phi = 1/2 at qp q>=1: q (4 -> node 0)
 #pragma unroll
         for (int a = 0; a < NV; a++) Facc[a] += Wi * k.F0[a] + JxW * k.F1[a];
 #pragma unroll
@@ -237,22 +256,21 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
           double m = 0.0;
           if (M::CMASK >> ab & 1u) m = Wi * k.C[a][b];
           if (M::TMASK >> ab & 1u) m += JxW * k.T[a][b];
-          if (q == 0) Kb[s] = 0.25 * m;
-          else { Kb[s] += (1.0 / 6.0) * m; Kx[q - 1][s] = (1.0 / 3.0) * m; }
+          Kb[s] += wb * m;
+          if (q > 0) xslot[(size_t)s * NEN * PAIRS] = (1.0 / 3.0) * m;
           if (M::SMASK >> ab & 1u) Ss[slot_of(M::SMASK, ab)] += JxW * k.S[a][b];
         }
       }
-      // stage my row: node j gets base + its own extra (+ stiffness part)
+      // complete my row: every node gets the base (+ stiffness part) on top of its own extra
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const int qx = j == 0 ? 3 : j - 1;  // qp k >= 1 that has phi = 1/2 at node j
 #pragma unroll
         for (int ab = 0; ab < VV; ab++) {
           if (!(KMASK >> ab & 1u)) continue;
           const int s = slot_of(KMASK, ab);
-          double v = Kb[s] + Kx[qx][s];
+          double v = Kb[s];
           if (M::SMASK >> ab & 1u) v += Ss[slot_of(M::SMASK, ab)] * GG[j];
-          stageK[((size_t)j * NKV + s) * PAIRS + tid] = v;
+          stageK[((size_t)s * NEN + j) * PAIRS + tid] += v;
         }
       }
     } else {
@@ -333,7 +351,7 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
 #pragma unroll
       for (int j = 0; j < NEN; j++)
 #pragma unroll
-        for (int s = 0; s < NKV; s++) stageK[((size_t)j * NKV + s) * PAIRS + tid] = Kacc[j][s];
+        for (int s = 0; s < NKV; s++) stageK[((size_t)s * NEN + j) * PAIRS + tid] = Kacc[j][s];
     }
 #pragma unroll
     for (int a = 0; a < NV; a++) stageF[a * PAIRS + tid] = Facc[a];
@@ -341,7 +359,8 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   __syncthreads();
 
   // ------------------------------------------------------------------ phase 2: one block per thread
-  const int blk0 = s_rowptr[0], nblk = s_rowptr[nnode] - blk0;
+  // Each block is the fixed-order sum of its contributors (ascending element id == the reference's serial loop
+  // order) and is written exactly once; consecutive threads write consecutive blocks of a row (row-local SoA).
   for (int b = tid; b < nblk; b += PAIRS) {
     const int B = blk0 + b;
     int lo = 0, hi = nnode;  // largest r with s_rowptr[r] <= B
@@ -349,24 +368,23 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
       const int mid = (lo + hi) >> 1;
       if (s_rowptr[mid] <= B) lo = mid; else hi = mid;
     }
-    const int L = s_rowptr[lo + 1] - s_rowptr[lo], kk = B - s_rowptr[lo];
+    const int r0 = s_rowptr[lo], L = s_rowptr[lo + 1] - r0, kk = B - r0;
     double acc[NKV > 0 ? NKV : 1];
 #pragma unroll
     for (int s = 0; s < NKV; s++) acc[s] = 0.0;
-    const int c0 = A.cptr[B], c1 = A.cptr[B + 1];
-    for (int c = c0; c < c1; c++) {
-      const unsigned code = A.clist[c];
-      const double* src = stageK + ((size_t)(code >> 12) * NKV) * PAIRS + (code & 0xfffu);
+    const int c1 = s_cptr[b + 1];
+    for (int c = s_cptr[b]; c < c1; c++) {
+      const double* src = stageK + s_clist[c];
 #pragma unroll
-      for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * PAIRS];
+      for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * NEN * PAIRS];
     }
-    double* dst = A.val + (size_t)s_rowptr[lo] * VV + kk;
+    double* dst = A.val + (size_t)r0 * VV + kk;
 #pragma unroll
     for (int ab = 0; ab < VV; ab++) dst[(size_t)ab * L] = (KMASK >> ab & 1u) ? acc[slot_of(KMASK, ab)] : 0.0;
   }
   for (int t = tid; t < nnode * NV; t += PAIRS) {
     const int r = t / NV, a = t - r * NV;
-    const int q0 = A.n2e_ptr[node0 + r] - pair0, q1 = A.n2e_ptr[node0 + r + 1] - pair0;
+    const int q0 = s_n2e[r], q1 = s_n2e[r + 1];
     double f = 0.0;
     for (int q = q0; q < q1; q++) f += stageF[a * PAIRS + q];
     A.rhs[(size_t)(node0 + r) * NV + a] = f;
@@ -383,11 +401,16 @@ __global__ void k_extract_diag(int n_owned, int nv, const int32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------- host launchers
-static void fill_pulse(Pulse& o, const double* p) { o.cM = p[0]; o.c0 = p[1]; o.c1 = p[2]; }
-static void fill_sd(StepDecay& o, const double* p) { o.cM = p[0]; o.c0 = p[1]; o.c1 = p[2]; o.slope = p[0] / (p[2] - p[1]); }
+// utils.h:104,116,162: a law with cM <= 0 returns 0 -> pass cM = 0 and zero slopes to the device
+static void fill_pulse(Pulse& o, const double* p) { o.cM = p[0] > 0.0 ? p[0] : 0.0; o.c0 = p[1]; o.c1 = p[2]; }
+static void fill_sd(StepDecay& o, const double* p) {
+  const bool on = p[0] > 0.0;
+  o.cM = on ? p[0] : 0.0; o.c0 = p[1]; o.c1 = p[2]; o.slope = on ? p[0] / (p[2] - p[1]) : 0.0;
+}
 static void fill_tr(Trapezoid& o, const double* p) {
-  o.cM = p[0]; o.c0 = p[1]; o.c1 = p[2]; o.c2 = p[3]; o.c3 = p[4];
-  o.up = p[0] / (p[2] - p[1]); o.dn = p[0] / (p[4] - p[3]);
+  const bool on = p[0] > 0.0;
+  o.cM = on ? p[0] : 0.0; o.c0 = p[1]; o.c1 = p[2]; o.c2 = p[3]; o.c3 = p[4];
+  o.up = on ? p[0] / (p[2] - p[1]) : 0.0; o.dn = on ? p[0] / (p[4] - p[3]) : 0.0;
 }
 
 template <class M, int NEN, int PAIRS, int MINB>
@@ -410,8 +433,16 @@ static int launch_t(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
 template <class M>
 static int launch_m(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
   if (c->etype == RDC_TET4) {
-    if constexpr (M::NV == 3) return launch_t<M, 4, 256, 2>(c, A, P);  // 3-variable models: 2 CTAs of 256 pairs per SM
-    else return launch_t<M, 4, 128, 2>(c, A, P);                       // 5-variable models: shared-memory stage of 128 pairs
+    if constexpr (M::NV == 3) {  // 3-variable models: 2 CTAs of 256 pairs or 4 CTAs of 128 pairs per SM
+      if (c->S.pairs_per_cta == 256) return launch_t<M, 4, 256, 2>(c, A, P);
+      static int minb = -1;
+      if (minb < 0) { const char* e = getenv("RDC_ASM_MINB"); minb = e ? atoi(e) : 4; }
+      if (minb == 5) return launch_t<M, 4, 128, 5>(c, A, P);
+      if (minb == 6) return launch_t<M, 4, 128, 6>(c, A, P);
+      return launch_t<M, 4, 128, 4>(c, A, P);
+    } else {
+      return launch_t<M, 4, 128, 2>(c, A, P);  // 5-variable models: shared-memory stage of 128 pairs
+    }
   }
   return launch_t<M, 8, 128, 1>(c, A, P);
 }
@@ -419,7 +450,11 @@ static int launch_m(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
 // pairs per assembly CTA (= block size); bounded by the shared-memory stage of nen*nkv+v doubles per pair
 int pairs_per_cta_for(int model, int etype) {
   const bool v5 = (model == RDC_PIHNA || model == RDC_PROTEAS);
-  if (etype == RDC_TET4) return v5 ? 128 : 256;
+  if (etype == RDC_TET4) {
+    if (v5) return 128;
+    const char* e = getenv("RDC_ASM_PAIRS");  // tuning knob: 128 or 256 pairs per CTA for the 3-variable models
+    return (e && atoi(e) == 128) ? 128 : 256;
+  }
   return 128;
 }
 
@@ -436,7 +471,10 @@ int launch_assemble(rdc_ctx* c) {
       AdpmParams P;
       P.dt2 = h;
       fill_pulse(P.decay_PrP, p + ADPM_DECAY_PRP);
-      P.decay_PrP.cM = p[ADPM_DECAY_PRP] * pow(c->time, p[ADPM_GAMMA]);  // adpm.C:369
+      {
+        const double cm = p[ADPM_DECAY_PRP] * pow(c->time, p[ADPM_GAMMA]);  // adpm.C:369
+        P.decay_PrP.cM = cm > 0.0 ? cm : 0.0;
+      }
       fill_pulse(P.diffuse_A, p + ADPM_DIFFUSE_AB); fill_pulse(P.taxis1_A, p + ADPM_TAXIS1_AB);
       fill_pulse(P.taxis2_A, p + ADPM_TAXIS2_AB); fill_sd(P.produce_A, p + ADPM_PRODUCE_AB);
       fill_tr(P.transform_A, p + ADPM_TRANSFORM_AB); fill_pulse(P.decay_A, p + ADPM_DECAY_AB);

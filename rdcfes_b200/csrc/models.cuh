@@ -42,27 +42,24 @@ __device__ __forceinline__ double dot3_rn(const double* a, const double* b) {
 }
 
 // ------------------------------------------------------------------------------------ rate laws
-// utils.h:100-110 (cM<=0 disables the law, Appendix C-7)
+// utils.h:100-110.  "cM <= 0 disables the law" (Appendix C-7) is applied on the host: the parameter structs
+// carry cM = 0 and zero slopes for disabled laws, so the device code needs no cM test.
 __device__ __forceinline__ double law_pulse(double C, double cM, double c0, double c1) {
-  return (cM > 0.0 && C >= c0 && C < c1) ? cM : 0.0;
+  return (C >= c0 && C < c1) ? cM : 0.0;
 }
 struct StepDecay { double cM, c0, c1, slope; };  // slope = cM/(c1-c0) precomputed on the host
 __device__ __forceinline__ void law_stepdecay(double C, const StepDecay& p, double& v, double& dv) {  // utils.h:112-133
   v = 0.0; dv = 0.0;
-  if (p.cM > 0.0) {
-    if (C < p.c0) v = p.cM;
-    else if (C < p.c1) { v = (p.c1 - C) * p.slope; dv = -p.slope; }
-  }
+  if (C < p.c0) v = p.cM;
+  else if (C < p.c1) { v = (p.c1 - C) * p.slope; dv = -p.slope; }
 }
 struct Trapezoid { double cM, c0, c1, c2, c3, up, dn; };  // up = cM/(c1-c0), dn = cM/(c3-c2)
 __device__ __forceinline__ void law_trapezoid(double C, const Trapezoid& p, double& v, double& dv) {  // utils.h:158-187
   v = 0.0; dv = 0.0;
-  if (p.cM > 0.0) {
-    if (C < p.c0) {}
-    else if (C < p.c1) { v = (C - p.c0) * p.up; dv = p.up; }
-    else if (C < p.c2) { v = p.cM; }
-    else if (C < p.c3) { v = (p.c3 - C) * p.dn; dv = -p.dn; }
-  }
+  if (C < p.c0) {}
+  else if (C < p.c1) { v = (C - p.c0) * p.up; dv = p.up; }
+  else if (C < p.c2) { v = p.cM; }
+  else if (C < p.c3) { v = (p.c3 - C) * p.dn; dv = -p.dn; }
 }
 struct Pulse { double cM, c0, c1; };
 

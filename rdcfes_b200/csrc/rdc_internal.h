@@ -43,7 +43,7 @@ struct HostSetup {
   std::vector<int32_t> diag_blk;                 // [n_owned] block index of the diagonal block
   std::vector<int32_t> cta_node;                 // [ncta+1] node ranges of the assembly CTAs
   std::vector<int32_t> cptr;                     // [nnzb+1] into clist
-  std::vector<uint16_t> clist;                   // (j << 12) | pair index inside the CTA
+  std::vector<uint16_t> clist;                   // j * pairs_per_cta + pair index inside the CTA
   int pairs_per_cta = 0;
   // halo exchange (distributed): ghosts are ordered by owner rank, so each neighbour's ghosts are contiguous
   std::vector<int> nbr_rank;                     // neighbours

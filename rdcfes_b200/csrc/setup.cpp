@@ -306,7 +306,7 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
         const int64_t le = S.pair[p] >> 3;
         for (int j = 0; j < nen; j++) {
           const int32_t k = (int32_t)(std::lower_bound(rc0, rc0 + len, S.conn[le * nen + j]) - rc0);
-          S.clist[(size_t)cur[k]++] = (uint16_t)((j << 12) | (p - pair0));
+          S.clist[(size_t)cur[k]++] = (uint16_t)(j * pairs_per_cta + (p - pair0));
         }
       }
     }

@@ -151,41 +151,54 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double*
   }
 }
 
-// out[k] = <V_k, w> for k < nvec (nvec <= MD_CHUNK) and, when with_norm, out[nvec] = <w, w>
+// out[k] = <V_k, w> for k < nvec (nvec <= 8*NCH) and, when with_norm, out[nvec] = <w, w>.  One pass over w and
+// the basis for the whole Gram-Schmidt column: up to 32 independent loads in flight per thread.
+template <int NCH>
 __global__ void __launch_bounds__(RED_THREADS) k_multidot(size_t n, int nvec, const double* __restrict__ V, size_t ldv,
                                                           const double* __restrict__ w, int with_norm, double* partial,
                                                           unsigned* counter, double* out, const int* __restrict__ done) {
   if (done && *done) return;
-  double acc[MD_CHUNK + 1];
+  constexpr int NA = 8 * NCH;
+  double acc[NA + 1];
 #pragma unroll
-  for (int k = 0; k <= MD_CHUNK; k++) acc[k] = 0.0;
+  for (int k = 0; k <= NA; k++) acc[k] = 0.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double wi = w[i];
+    double v[NA];
 #pragma unroll
-    for (int k = 0; k < MD_CHUNK; k++)
-      if (k < nvec) acc[k] = fma(V[(size_t)k * ldv + i], wi, acc[k]);
-    if (with_norm) acc[MD_CHUNK] = fma(wi, wi, acc[MD_CHUNK]);
+    for (int k = 0; k < NA; k++) v[k] = (k < nvec) ? V[(size_t)k * ldv + i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NA; k++) acc[k] = fma(v[k], wi, acc[k]);
+    acc[NA] = fma(wi, wi, acc[NA]);
   }
   if (with_norm) {  // place the norm right after the dots
-    double nn = acc[MD_CHUNK];
+    const double nn = acc[NA];
 #pragma unroll
-    for (int k = 0; k < MD_CHUNK; k++)
+    for (int k = 0; k < NA; k++)
       if (k == nvec) acc[k] = nn;
-    if (nvec == MD_CHUNK) acc[MD_CHUNK] = nn;
   }
-  grid_reduce<MD_CHUNK + 1>(acc, nvec + (with_norm ? 1 : 0), partial, counter, out);
+  grid_reduce<NA + 1>(acc, nvec + (with_norm ? 1 : 0), partial, counter, out);
 }
 
-// w -= sum_k h[k] V_k (k < nvec) ; out[0] = ||w||^2
+// w -= sum_k h[k] V_k (k < nvec <= 8*NCH) ; out[0] = ||w||^2
+template <int NCH>
 __global__ void __launch_bounds__(RED_THREADS) k_gs_update(size_t n, int nvec, const double* __restrict__ V, size_t ldv,
                                                            double* __restrict__ w, const double* __restrict__ h,
                                                            double* partial, unsigned* counter, double* out,
                                                            const int* __restrict__ done) {
   if (done && *done) return;
+  constexpr int NA = 8 * NCH;
+  double hk[NA];
+#pragma unroll
+  for (int k = 0; k < NA; k++) hk[k] = (k < nvec) ? h[k] : 0.0;
   double acc[1] = {0.0};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     double wi = w[i];
-    for (int k = 0; k < nvec; k++) wi = fma(-h[k], V[(size_t)k * ldv + i], wi);
+    double v[NA];
+#pragma unroll
+    for (int k = 0; k < NA; k++) v[k] = (k < nvec) ? V[(size_t)k * ldv + i] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NA; k++) wi = fma(-hk[k], v[k], wi);
     w[i] = wi;
     acc[0] = fma(wi, wi, acc[0]);
   }
@@ -420,7 +433,7 @@ int solver_init(rdc_ctx* c) {
   const size_t vb = W->vec_len * sizeof(double);
   RDC_CUDA(cudaMalloc(&W->t0, vb)); RDC_CUDA(cudaMalloc(&W->t1, vb));
   RDC_CUDA(cudaMemsetAsync(W->t0, 0, vb, c->stream)); RDC_CUDA(cudaMemsetAsync(W->t1, 0, vb, c->stream));
-  RDC_CUDA(cudaMalloc(&W->partial, sizeof(double) * RED_BLOCKS * (MD_CHUNK + 1)));
+  RDC_CUDA(cudaMalloc(&W->partial, sizeof(double) * RED_BLOCKS * 33));
   RDC_CUDA(cudaMalloc(&W->counter, sizeof(unsigned)));
   RDC_CUDA(cudaMemsetAsync(W->counter, 0, sizeof(unsigned), c->stream));
   RDC_CUDA(cudaMalloc(&W->scal, sizeof(double) * 32));
@@ -477,18 +490,40 @@ static int multidot(rdc_ctx* c, int nvec, const double* V, const double* w, bool
   SolverWork* W = c->work;
   const size_t n = (size_t)c->S.n_owned * c->nv;
   int done_cols = 0;
-  while (done_cols < nvec || (nvec == 0 && with_norm && done_cols == 0)) {
-    const int chunk = nvec - done_cols < MD_CHUNK ? nvec - done_cols : MD_CHUNK;
-    const bool last = (done_cols + chunk == nvec);
-    k_multidot<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, V + (size_t)done_cols * W->vec_len, W->vec_len, w,
-                                                         (with_norm && last) ? 1 : 0, W->partial, W->counter,
-                                                         W->h + done_cols, W->state);
+  do {
+    const int chunk = nvec - done_cols < 32 ? nvec - done_cols : 32;
+    const int wn = (with_norm && done_cols + chunk == nvec) ? 1 : 0;
+    const double* Vc = V + (size_t)done_cols * W->vec_len;
+    double* out = W->h + done_cols;
+    if (chunk <= 8) k_multidot<1><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, wn, W->partial, W->counter, out, W->state);
+    else if (chunk <= 16) k_multidot<2><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, wn, W->partial, W->counter, out, W->state);
+    else if (chunk <= 24) k_multidot<3><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, wn, W->partial, W->counter, out, W->state);
+    else k_multidot<4><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, wn, W->partial, W->counter, out, W->state);
     c->st.kernel_launches++;
     RDC_CUDA(cudaGetLastError());
     done_cols += chunk;
-    if (nvec == 0) break;
-  }
+  } while (done_cols < nvec);
   return allreduce_sum(c, W->h, nvec + (with_norm ? 1 : 0));
+}
+
+// w -= V[0..nvec) h ; ||w||^2 -> out
+static int gs_update(rdc_ctx* c, int nvec, const double* V, double* w, const double* h, double* out) {
+  SolverWork* W = c->work;
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  int done_cols = 0;
+  do {
+    const int chunk = nvec - done_cols < 32 ? nvec - done_cols : 32;
+    const double* Vc = V + (size_t)done_cols * W->vec_len;
+    const double* hc = h + done_cols;
+    if (chunk <= 8) k_gs_update<1><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, hc, W->partial, W->counter, out, W->state);
+    else if (chunk <= 16) k_gs_update<2><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, hc, W->partial, W->counter, out, W->state);
+    else if (chunk <= 24) k_gs_update<3><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, hc, W->partial, W->counter, out, W->state);
+    else k_gs_update<4><<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, chunk, Vc, W->vec_len, w, hc, W->partial, W->counter, out, W->state);
+    c->st.kernel_launches++;
+    RDC_CUDA(cudaGetLastError());
+    done_cols += chunk;
+  } while (done_cols < nvec);
+  return 0;
 }
 
 static int poll(rdc_ctx* c) {
@@ -539,9 +574,7 @@ static int gmres(rdc_ctx* c, const double* scale, double rtol, int maxits, int m
       if ((rc = halo_exchange(c, vj))) return rc;
       if ((rc = launch_spmv(c, vj, vn, scale, true))) return rc;         // vn = B A vj
       if ((rc = multidot(c, j + 1, W->V, vn, false))) return rc;    // classical Gram-Schmidt: all dots first
-      k_gs_update<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, j + 1, W->V, ld, vn, W->h, W->partial, W->counter,
-                                                            W->h + 512, W->state);
-      c->st.kernel_launches++;
+      if ((rc = gs_update(c, j + 1, W->V, vn, W->h, W->h + 512))) return rc;
       if ((rc = allreduce_sum(c, W->h + 512, 1))) return rc;
       k_gmres_givens<<<1, 1, 0, c->stream>>>(j, m, W->h, W->h + 512, W->H, W->cs, W->sn, W->g, W->scal, W->state);
       k_scale_dev<<<grid_for(n), 256, 0, c->stream>>>(n, vn, W->scal + 3, W->state);

@@ -34,7 +34,7 @@ EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_dis
            "rdc_update_coords", "rdc_set_solution", "rdc_get_solution", "rdc_get_old_solution", "rdc_n_dofs",
            "rdc_set_time", "rdc_set_dt", "rdc_rotate", "rdc_assemble", "rdc_solve", "rdc_clamp", "rdc_step",
            "rdc_spmv", "rdc_bench_spmv", "rdc_download_csr", "rdc_free", "rdc_get_stats", "rdc_set_stream",
-           "rdc_version"]
+           "rdc_version", "rdc_probe_partition"]
 
 
 def load():

@@ -192,3 +192,35 @@ class TransientRdcSystem:
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._L.rdc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+
+def probe_partition(elem_type, nvars, conn, xyz, rank, nranks, partitioner=0):
+    """Host-only view of the partition / halo lists of one rank (rdc_probe_partition); needs no GPU."""
+    L = _lib.load()
+    conn = np.ascontiguousarray(conn, dtype=np.int32)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n_owned, n_ghost, n_nbr = C.c_int32(), C.c_int32(), C.c_int32()
+    n_el = C.c_int64()
+    ptrs = [C.c_void_p() for _ in range(6)]
+    L.rdc_probe_partition.restype = C.c_int
+    rc = L.rdc_probe_partition(C.c_int(elem_type), C.c_int(nvars), C.c_int64(xyz.shape[0]), C.c_int64(conn.shape[0]),
+                               _ptr(conn), _ptr(xyz), C.c_int(rank), C.c_int(nranks), C.c_int(partitioner),
+                               C.byref(n_owned), C.byref(n_ghost), C.byref(n_el), C.byref(ptrs[0]), C.byref(n_nbr),
+                               C.byref(ptrs[1]), C.byref(ptrs[2]), C.byref(ptrs[3]), C.byref(ptrs[4]), C.byref(ptrs[5]))
+    if rc:
+        raise _lib.RdcError(rc, L.rdc_last_error(None).decode())
+
+    def take(p, n):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(max(n, 1),))[:n].copy()
+        L.rdc_free(p)
+        return a
+
+    nn = n_nbr.value
+    owner = take(ptrs[0], xyz.shape[0])
+    nbr = take(ptrs[1], nn)
+    send_ptr = take(ptrs[2], nn + 1)
+    send_glob = take(ptrs[3], int(send_ptr[-1]) if nn else 0)
+    recv_ptr = take(ptrs[4], nn + 1)
+    recv_glob = take(ptrs[5], n_ghost.value)
+    return dict(n_owned=n_owned.value, n_ghost=n_ghost.value, n_elems_local=n_el.value, owner=owner, nbr=nbr,
+                send_ptr=send_ptr, send_glob=send_glob, recv_ptr=recv_ptr, recv_glob=recv_glob)

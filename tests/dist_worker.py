@@ -1,0 +1,81 @@
+"""torchrun worker of the multi-GPU parity test: every rank drives the same problem through
+rdc_create_distributed (METIS or RCB node partition, NCCL halo exchange + all-reduce); rank 0 compares the
+gathered solution and the owned operator rows with the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import cases  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oracle import oracle as O
+    from rdcfes_b200 import system as rs
+    buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    failures = []
+    for model, ksp, partitioner, nsteps in ((cases.ADPM, 0, 0, 3), (cases.PIHNA, 0, 1, 2), (cases.RIPF, 2, 0, 12),
+                                            (cases.HCC, 2, 1, 2)):
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(rs.make_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+        length = 50.0 if model == cases.RIPF else 1.0
+        conn, xyz = cases.mesh(cases.TET4, 7, distort=0.2, length=length)
+        p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+        gpu = cases.gpu_system(model, cases.TET4, conn, xyz, p, u0, ef, nf, device=local, rank=rank, nranks=world,
+                               partitioner=partitioner, unique_id=uid)
+        gpu.ksp = ksp
+        orc = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf) if rank == 0 else None
+        dt = cases.DT[model]
+        # operator rows owned by this rank against the oracle (every rank checks its own rows)
+        gpu.rotate()
+        gpu.assemble(dt, dt)
+        rows, rowptr, col, val, rhs = gpu.download_csr()
+        o2 = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf)
+        o2.u_old = o2.u.copy()
+        val_o, rhs_o = o2.assemble(dt, dt)
+        for k, r in enumerate(rows):
+            a, b = o2.rowptr[r], o2.rowptr[r + 1]
+            if not np.array_equal(col[rowptr[k]:rowptr[k + 1]], o2.col[a:b]):
+                failures.append(f"{cases.NAMES[model]}: pattern of row {r}")
+                break
+        ref = np.concatenate([val_o[o2.rowptr[r]:o2.rowptr[r + 1]] for r in rows])
+        if (np.abs(val - ref) / cases.csr_tolerance(val_o)[: 1].max()).max() > 1.0 and \
+                (np.abs(val - ref) > 1e-12 * np.maximum(np.abs(ref), 1e-3 * np.abs(val_o).max())).any():
+            failures.append(f"{cases.NAMES[model]}: K rows differ on rank {rank}")
+        if np.abs(rhs - rhs_o[rows]).max() > 1e-12 * np.abs(rhs_o).max():
+            failures.append(f"{cases.NAMES[model]}: F differs on rank {rank}")
+        for _ in range(nsteps):
+            gpu.step(dt)
+            if rank == 0:
+                orc.step(dt, pc=O.PC_ILU)
+        u = gpu.get_solution()
+        if rank == 0:
+            rel = np.linalg.norm(u - orc.u) / np.linalg.norm(orc.u)
+            st = gpu.stats()
+            print(f"{cases.NAMES[model]} x{world}: rel L2 vs oracle after {nsteps} steps {rel:.2e}; owned {st.n_nodes_local} "
+                  f"ghost {st.n_nodes_ghost}", flush=True)
+            if not rel <= 1e-8:
+                failures.append(f"{cases.NAMES[model]}: solution rel L2 {rel:.3e}")
+        gpu.close()
+    flag = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(flag)
+    if failures:
+        print(f"rank {rank} FAILURES: {failures}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()
