@@ -42,6 +42,7 @@ def main():
         gpu.rotate()
         gpu.assemble(dt, dt)
         rows, rowptr, col, val, rhs = gpu.download_csr()
+        gpu.time = 0.0  # assemble(time, dt) set system.time; the time loop below starts again from t = 0
         o2 = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf)
         o2.u_old = o2.u.copy()
         val_o, rhs_o = o2.assemble(dt, dt)
@@ -56,10 +57,16 @@ def main():
             failures.append(f"{cases.NAMES[model]}: K rows differ on rank {rank}")
         if np.abs(rhs - rhs_o[rows]).max() > 1e-12 * np.abs(rhs_o).max():
             failures.append(f"{cases.NAMES[model]}: F differs on rank {rank}")
+        trace = []
         for _ in range(nsteps):
-            gpu.step(dt)
+            its, res = gpu.step(dt)
             if rank == 0:
-                orc.step(dt, pc=O.PC_ILU)
+                oits, ores = orc.step(dt, pc=O.PC_ILU)
+                trace.append((its, oits, float(np.linalg.norm(gpu.get_solution() - orc.u) / np.linalg.norm(orc.u))))
+            else:
+                gpu.get_solution()
+        if rank == 0:
+            print("   trace (gpu its, oracle its, rel err):", trace, flush=True)
         u = gpu.get_solution()
         if rank == 0:
             rel = np.linalg.norm(u - orc.u) / np.linalg.norm(orc.u)
