@@ -52,42 +52,83 @@ struct SolverWork {
 namespace rdc {
 
 // ------------------------------------------------------------------------------------------ SpMV
-// Half-warp per block row; lane k owns block k of the row (row-local SoA layout -> every load of a
-// half-warp is one contiguous segment).  rowscale != nullptr fuses the Jacobi scaling: y = D^-1 (A x).
-template <int NV>
-__global__ void __launch_bounds__(256) k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+// G lanes per block row; lane k owns blocks k, k+G, ... of the row (row-local SoA layout -> every load of a
+// lane group is one contiguous segment).  The operator is streamed once (read-only, no L1 allocation) while
+// the gathered x stays cacheable.  rowscale != nullptr fuses the Jacobi scaling: y = D^-1 (A x).
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <int NV, int G, int R>
+__global__ void __launch_bounds__(256, (NV == 3 && R == 1) ? 8 : 1) k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                               const double* __restrict__ val, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ rowscale,
                                               const int* __restrict__ done) {
   if (done && *done) return;
-  const int lane16 = threadIdx.x & 15;
-  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 4);
-  double acc[NV];
+  const int lane = threadIdx.x & (G - 1);
+  const int grp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
+  // R consecutive rows per lane group: the loads of all R rows are issued before any is consumed
+  int r0[R], L[R];
 #pragma unroll
-  for (int a = 0; a < NV; a++) acc[a] = 0.0;
-  if (row < n_rows) {
-    const int r0 = rowptr[row], L = rowptr[row + 1] - r0;
-    const double* v0 = val + (size_t)r0 * (NV * NV);
-    for (int k = lane16; k < L; k += 16) {
-      const int c = col[r0 + k];
+  for (int q = 0; q < R; q++) {
+    const int row = grp * R + q;
+    r0[q] = row < n_rows ? rowptr[row] : 0;
+    L[q] = row < n_rows ? rowptr[row + 1] - r0[q] : 0;
+  }
+  double acc[R][NV];
+#pragma unroll
+  for (int q = 0; q < R; q++)
+#pragma unroll
+    for (int a = 0; a < NV; a++) acc[q][a] = 0.0;
+  int kmax = 0;
+#pragma unroll
+  for (int q = 0; q < R; q++) kmax = max(kmax, L[q]);
+  for (int k = lane; k < kmax; k += G) {
+    int c[R];
+    double a_[R][NV * NV];
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const bool on = k < L[q];
+      c[q] = on ? ld_stream_i32(col + r0[q] + k) : 0;
+      const double* v0 = val + (size_t)r0[q] * (NV * NV);
+#pragma unroll
+      for (int e = 0; e < NV * NV; e++) a_[q][e] = on ? ld_stream(v0 + (size_t)e * L[q] + k) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < R; q++) {
       double xv[NV];
 #pragma unroll
-      for (int b = 0; b < NV; b++) xv[b] = x[(size_t)c * NV + b];
+      for (int b = 0; b < NV; b++) xv[b] = x[(size_t)c[q] * NV + b];
 #pragma unroll
       for (int a = 0; a < NV; a++)
 #pragma unroll
-        for (int b = 0; b < NV; b++) acc[a] = fma(v0[(size_t)(a * NV + b) * L + k], xv[b], acc[a]);
+        for (int b = 0; b < NV; b++) acc[q][a] = fma(a_[q][a * NV + b], xv[b], acc[q][a]);
     }
   }
 #pragma unroll
-  for (int off = 8; off > 0; off >>= 1)
+  for (int off = G / 2; off > 0; off >>= 1)
 #pragma unroll
-    for (int a = 0; a < NV; a++) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], off, 16);
-  if (row < n_rows && lane16 == 0) {
+    for (int q = 0; q < R; q++)
 #pragma unroll
-    for (int a = 0; a < NV; a++) {
-      const size_t o = (size_t)row * NV + a;
-      y[o] = rowscale ? acc[a] * rowscale[o] : acc[a];
+      for (int a = 0; a < NV; a++) acc[q][a] += __shfl_xor_sync(0xffffffffu, acc[q][a], off, G);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int row = grp * R + q;
+      if (row < n_rows) {
+#pragma unroll
+        for (int a = 0; a < NV; a++) {
+          const size_t o = (size_t)row * NV + a;
+          y[o] = rowscale ? acc[q][a] * rowscale[o] : acc[q][a];
+        }
+      }
     }
   }
 }
@@ -95,14 +136,20 @@ __global__ void __launch_bounds__(256) k_spmv(int n_rows, const int32_t* __restr
 int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done) {
   const int n = c->S.n_owned;
   const int* done = (check_done && c->work) ? c->work->state : nullptr;
-  const unsigned grid = (unsigned)(((size_t)n * 16 + 255) / 256);
+  static int R = -1;
+  if (R < 0) { const char* e = getenv("RDC_SPMV_R"); R = e ? atoi(e) : 1; if (R != 1 && R != 2 && R != 4) R = 1; }
+  constexpr int G = 16;
+  const size_t ngroups = ((size_t)n + R - 1) / R;
+  const unsigned grid = (unsigned)((ngroups * G + 255) / 256);
   // every SpMV launch of a solve is bracketed by its own event pair (summed after the solve) so that the
   // roofline of the dominant kernel is measured live, inside the timed step
   SolverWork* W = c->work;
   const bool timed = check_done && W && W->n_ev_used < SolverWork::MAX_EV;
   if (timed) cudaEventRecord(W->ev[2 * W->n_ev_used], c->stream);
-  if (c->nv == 3) k_spmv<3><<<grid, 256, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, done);
-  else k_spmv<5><<<grid, 256, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, done);
+#define RDC_SPMV_LAUNCH(NVV, RR) k_spmv<NVV, G, RR><<<grid, 256, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, done)
+  if (c->nv == 3) { if (R == 1) RDC_SPMV_LAUNCH(3, 1); else if (R == 2) RDC_SPMV_LAUNCH(3, 2); else RDC_SPMV_LAUNCH(3, 4); }
+  else { if (R == 1) RDC_SPMV_LAUNCH(5, 1); else RDC_SPMV_LAUNCH(5, 2); }
+#undef RDC_SPMV_LAUNCH
   if (timed) { cudaEventRecord(W->ev[2 * W->n_ev_used + 1], c->stream); W->n_ev_used++; }
   c->st.kernel_launches++;
   c->st.n_spmv++;
@@ -698,13 +745,41 @@ static int pcg(rdc_ctx* c, const double* scale, double rtol, int maxits, int* it
   return 0;
 }
 
-// BiCGStab scalar steps (left-preconditioned system B A x = B b)
-__global__ void k_bi_rho(const double* d, double* S, int* state, int first) {  // rho = <r0, r>; beta
-  if (state[0]) return;
-  S[S_RHO_OLD] = S[S_RHO];
-  S[S_RHO] = d[0];
-  S[S_BETA] = first ? 0.0 : (S[S_RHO] / S[S_RHO_OLD]) * (S[S_ALPHA] / S[S_OMEGA]);
-  S[S_TMP] = -S[S_BETA] * S[S_OMEGA];
+// ---- BiCGStab on the left-preconditioned system B A x = B b: fused vector kernels, scalars on the device ----
+// p = r + beta (p - omega v)
+__global__ void k_bi_p(size_t n, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p,
+                       const double* __restrict__ S, const int* __restrict__ done) {
+  if (*done) return;
+  const double beta = S[S_BETA], omega = S[S_OMEGA];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+}
+// s = r - alpha v
+__global__ void k_bi_s(size_t n, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ s,
+                       const double* __restrict__ S, const int* __restrict__ done) {
+  if (*done) return;
+  const double alpha = S[S_ALPHA];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s[i] = fma(-alpha, v[i], r[i]);
+}
+// x += alpha p + omega s ; r = s - omega t ; out = {<r0,r>, <r,r>}
+__global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, double* __restrict__ x, const double* __restrict__ p,
+                                                       const double* __restrict__ s, const double* __restrict__ t,
+                                                       double* __restrict__ r, const double* __restrict__ r0,
+                                                       const double* __restrict__ S, double* partial, unsigned* counter,
+                                                       double* out, const int* __restrict__ done) {
+  if (*done) return;
+  const double alpha = S[S_ALPHA], omega = S[S_OMEGA];
+  double acc[2] = {0.0, 0.0};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double si = s[i];
+    x[i] = fma(omega, si, fma(alpha, p[i], x[i]));
+    const double ri = fma(-omega, t[i], si);
+    r[i] = ri;
+    acc[0] = fma(r0[i], ri, acc[0]);
+    acc[1] = fma(ri, ri, acc[1]);
+  }
+  grid_reduce<2>(acc, 2, partial, counter, out);
 }
 __global__ void k_bi_alpha(const double* d, double* S, int* state) {  // alpha = rho / <r0, v>
   if (state[0]) return;
@@ -714,20 +789,29 @@ __global__ void k_bi_omega(const double* d, double* S, int* state) {  // omega =
   if (state[0]) return;
   S[S_OMEGA] = d[1] != 0.0 ? d[0] / d[1] : 0.0;
 }
-__global__ void k_bi_res(const double* d, double* S, int* state) {
+// after the x/r update: rho, beta for the next iteration, residual norm, convergence / breakdown
+__global__ void k_bi_next(const double* d, double* S, int* state) {
   if (state[0]) return;
-  const double res = sqrt(d[0]);
+  const double rho_old = S[S_RHO], rho = d[0];
+  S[S_RHO_OLD] = rho_old;
+  S[S_RHO] = rho;
+  S[S_BETA] = (rho / rho_old) * (S[S_ALPHA] / S[S_OMEGA]);
+  const double res = sqrt(d[1]);
   S[S_RES] = res;
   state[1] += 1;
-  if (!(res == res) || S[S_OMEGA] == 0.0) { state[0] = 1; state[3] = (res <= S[S_TARGET]) ? 0 : 1; }
+  if (!(res == res)) { state[0] = 1; state[3] = 1; }
   else if (res <= S[S_TARGET]) state[0] = 1;
+  else if (S[S_OMEGA] == 0.0 || rho == 0.0) { state[0] = 1; state[3] = 1; }
+}
+__global__ void k_bi_init(const double* d, double* S) {  // rho = <r0,r0> ; res = ||r0||
+  S[S_RHO] = d[0]; S[S_RHO_OLD] = d[0]; S[S_BETA] = 0.0; S[S_OMEGA] = 0.0; S[S_ALPHA] = 0.0; S[S_RES] = sqrt(d[0]);
 }
 
 static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
   SolverWork* W = c->work;
   int rc = ensure_extra_vectors(c);
   if (rc) return rc;
-  rc = ensure_gmres(c, 2);  // borrow V for three more vectors
+  rc = ensure_gmres(c, 2);  // borrow V for two more vectors
   if (rc) return rc;
   const size_t n = (size_t)c->S.n_owned * c->nv;
   static int sync_every = -1;
@@ -745,39 +829,28 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
   RDC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), c->stream));
   RDC_CUDA(cudaMemsetAsync(v, 0, n * sizeof(double), c->stream));
   if ((rc = multidot(c, 0, r, r, true))) return rc;
+  k_bi_init<<<1, 1, 0, c->stream>>>(W->h, W->scal);
+  c->st.kernel_launches++;
   if ((rc = poll(c))) return rc;
-  {
-    double h0;
-    RDC_CUDA(cudaMemcpy(&h0, W->h, sizeof(double), cudaMemcpyDeviceToHost));
-    if (sqrt(h0) <= W->h_scal[S_TARGET]) { *its_out = 0; *res_out = sqrt(h0); c->st.resnorm0 = W->h_scal[5]; return 0; }
-  }
+  if (W->h_scal[S_RES] <= W->h_scal[S_TARGET]) { *its_out = 0; *res_out = W->h_scal[S_RES]; c->st.resnorm0 = W->h_scal[5]; return 0; }
   int its = 0;
   while (its < maxits) {
-    if ((rc = multidot(c, 1, r0, r, false))) return rc;
-    k_bi_rho<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state, its == 0);
-    c->st.kernel_launches++;
-    // p = r + beta (p - omega v)  ==  p = beta p + (-beta omega) v + r
-    if ((rc = axpby(c, n, v, p, S_TMP, 1.0, S_BETA, 1.0))) return rc;
-    if ((rc = axpby(c, n, r, p, -1, 1.0, -1, 1.0))) return rc;
+    k_bi_p<<<grid_for(n), 256, 0, c->stream>>>(n, r, v, p, W->scal, W->state);
     if ((rc = halo_exchange(c, p))) return rc;
-    if ((rc = launch_spmv(c, p, v, scale, true))) return rc;                       // v = B A p
-    if ((rc = multidot(c, 1, r0, v, false))) return rc;
+    if ((rc = launch_spmv(c, p, v, scale, true))) return rc;                 // v = B A p
+    if ((rc = multidot(c, 1, r0, v, false))) return rc;                      // <r0, v>
     k_bi_alpha<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
-    c->st.kernel_launches++;
-    RDC_CUDA(cudaMemcpyAsync(s, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    if ((rc = axpby(c, n, v, s, S_ALPHA, -1.0, -1, 1.0))) return rc;         // s = r - alpha v
+    k_bi_s<<<grid_for(n), 256, 0, c->stream>>>(n, r, v, s, W->scal, W->state);
     if ((rc = halo_exchange(c, s))) return rc;
-    if ((rc = launch_spmv(c, s, t, scale, true))) return rc;                       // t = B A s
-    if ((rc = multidot(c, 1, s, t, true))) return rc;                        // <t,s>, <t,t>
+    if ((rc = launch_spmv(c, s, t, scale, true))) return rc;                 // t = B A s
+    if ((rc = multidot(c, 1, s, t, true))) return rc;                        // <s,t>, <t,t>
     k_bi_omega<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
-    c->st.kernel_launches++;
-    if ((rc = axpby(c, n, p, c->d_u, S_ALPHA, 1.0, -1, 1.0))) return rc;     // x += alpha p + omega s
-    if ((rc = axpby(c, n, s, c->d_u, S_OMEGA, 1.0, -1, 1.0))) return rc;
-    RDC_CUDA(cudaMemcpyAsync(r, s, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    if ((rc = axpby(c, n, t, r, S_OMEGA, -1.0, -1, 1.0))) return rc;         // r = s - omega t
-    if ((rc = multidot(c, 0, r, r, true))) return rc;
-    k_bi_res<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
-    c->st.kernel_launches++;
+    k_bi_xr<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, c->d_u, p, s, t, r, r0, W->scal, W->partial, W->counter,
+                                                      W->h + 64, W->state);
+    if ((rc = allreduce_sum(c, W->h + 64, 2))) return rc;
+    k_bi_next<<<1, 1, 0, c->stream>>>(W->h + 64, W->scal, W->state);
+    c->st.kernel_launches += 6;
+    RDC_CUDA(cudaGetLastError());
     its++;
     if (its % sync_every == 0 || its >= maxits) {
       if ((rc = poll(c))) return rc;
