@@ -6,7 +6,7 @@
 Workload (BASELINE.json metric, SURVEY.md 8d case S1): ADPM operators (parameter set P-full: every term
 active) on the synthetic unit-cube Kuhn-tet mesh n=119 -> 10 110 954 tets, 1 728 000 nodes, 5.18 M dofs,
 dt = 0.05.  One "step" = one pass of the time-loop body adpm.C:63-76: rotate time levels, assemble K and F,
-GMRES(30)+Jacobi solve to rtol 1e-12, check_solution.
+Krylov solve (BiCGStab + Jacobi by default, --ksp 0 = libMesh's GMRES(30)) to rtol 1e-12, check_solution.
   * value : device-resident steps/s (inputs in HBM when the timed region starts), CUDA events, max over ranks
   * e2e   : the same step through the C ABI with HOST buffers every step: rdc_set_solution (pinned H2D) ->
             rdc_step -> rdc_get_solution (D2H)
@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=119, help="cells per edge (119 -> 10.1 M tets)")
     ap.add_argument("--cpu-n", type=int, default=40, help="sample mesh of the CPU baseline")
-    ap.add_argument("--ksp", type=int, default=0)
+    ap.add_argument("--ksp", type=int, default=2, help="0 GMRES(30) (libMesh default), 1 CG, 2 BiCGStab; all Jacobi, rtol 1e-12")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partitioner", type=int, default=0)
     args = ap.parse_args()
@@ -242,8 +242,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"S1 ADPM P-full, unit-cube Kuhn tets n={args.n} ({E} tets, {N} nodes, {3 * N} dofs), "
-                               f"dt={DT}, GMRES(30)+Jacobi rtol 1e-12" if args.ksp == 0 else
-                               f"S1 ADPM P-full n={args.n} ({E} tets), ksp={args.ksp}+Jacobi rtol 1e-12",
+                               f"dt={DT}, {('GMRES(30)', 'CG', 'BiCGStab')[args.ksp]}+Jacobi rtol 1e-12",
                    "parallelism": f"node partition x{world} (METIS), NCCL halo + allreduce" if world > 1 else "single GPU",
                    "l2": "operator (1.9 GB) and vectors far exceed the 126 MB L2; no flush needed between steps",
                    "setup_s": round(t_setup, 2)},

@@ -42,7 +42,7 @@ extern "C" void rdc_free(void* p) { free(p); }
 
 template <class T>
 static int upload(rdc_ctx* c, T** dst, const std::vector<T>& src) {
-  const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T) + 64;  // slack: bulk copies round up to 16 B
   RDC_CUDA(cudaMalloc((void**)dst, bytes));
   if (!src.empty()) RDC_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
   return 0;
@@ -73,6 +73,9 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
   c->model = model; c->etype = elem_type; c->nen = elem_type == RDC_TET4 ? 4 : 8; c->nv = nv;
   c->nqp = elem_type == RDC_TET4 ? 5 : 8;
   c->device = device;
+  c->kmask = model_kmask(model);
+  c->nkv = __builtin_popcount(c->kmask);
+  if (!spmv_masks_ok()) { g_create_err = "internal: SpMV entry masks differ from the model definitions"; delete c; return RDC_E_STATE; }
   int rc = 0;
   auto fail = [&](int code) { g_create_err = c->err; rdc_destroy(c); return code; };
   try {
@@ -94,6 +97,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
 
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return fail(RDC_E_CUDA); }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  for (int k = 0; k < 2; k++) { cudaEventCreate(&c->ev_asm[k]); cudaEventCreate(&c->ev_sol[k]); cudaEventCreate(&c->ev_clamp[k]); }
   if (upload_fe_tables()) { c->err = "cannot upload the reference-element tables"; return fail(RDC_E_CUDA); }
 
   auto go = [&]() -> int {
@@ -138,7 +142,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     RDC_CUDA(cudaMemsetAsync(c->d_uolder, 0, vb, c->stream));
     RDC_CUDA(cudaMalloc(&c->d_rhs, (size_t)S.n_owned * nv * sizeof(double)));
     RDC_CUDA(cudaMalloc(&c->d_dinv, (size_t)S.n_owned * nv * sizeof(double)));
-    RDC_CUDA(cudaMalloc(&c->d_val, (size_t)c->nnzb * nv * nv * sizeof(double)));
+    RDC_CUDA(cudaMalloc(&c->d_val, (size_t)c->nnzb * c->nkv * sizeof(double) + 64));
     RDC_CUDA(cudaMalloc(&c->d_stage, (size_t)c->D_glob * sizeof(double)));
     if (model == RDC_RIPF) {
       RDC_CUDA(cudaMalloc(&c->d_td, (size_t)S.n_loc * 3 * sizeof(double)));
@@ -163,8 +167,10 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     const int64_t Nl = S.n_loc, El = S.E_loc, nnzb = c->nnzb, No = S.n_owned;
     const int f_e = model == RDC_ADPM ? 3 : 0;
     const int f_n = model == RDC_RIPF ? 3 : (model == RDC_PROTEAS ? 2 : 0);
-    c->st.bytes_assemble = 4LL * c->nen * El + 24LL * Nl + 8LL * nv * Nl + 8LL * f_e * El + 8LL * f_n * Nl + 8LL * nv * nv * nnzb + 8LL * nv * No;
-    c->st.bytes_spmv = nnzb * (8LL * nv * nv + 4) + 4LL * (No + 1) + 16LL * nv * No;
+    // operator entries are counted in the format actually traversed: NKV stored planes per block, not v*v
+    const int64_t nkv = c->nkv;
+    c->st.bytes_assemble = 4LL * c->nen * El + 24LL * Nl + 8LL * nv * Nl + 8LL * f_e * El + 8LL * f_n * Nl + 8LL * nkv * nnzb + 8LL * nv * No;
+    c->st.bytes_spmv = nnzb * (8LL * nkv + 4) + 4LL * (No + 1) + 16LL * nv * No;
     c->st.bytes_index = 4LL * (int64_t)S.pair.size() + 4LL * (No + 1) * 2 + 32LL * ((int64_t)S.cta_node.size() - 1) + 4LL * (nnzb + 1) +
                         2LL * (int64_t)S.clist.size();
     c->st.n_nodes_local = No; c->st.n_nodes_ghost = S.n_ghost; c->st.n_elems_local = El; c->st.nnzb_local = nnzb;
@@ -206,6 +212,11 @@ extern "C" void rdc_destroy(rdc_ctx* c) {
   cudaFree(c->d_prev); cudaFree(c->d_aux); cudaFree(c->d_send_idx); cudaFree(c->d_sendbuf);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  for (int k = 0; k < 2; k++) {
+    if (c->ev_asm[k]) cudaEventDestroy(c->ev_asm[k]);
+    if (c->ev_sol[k]) cudaEventDestroy(c->ev_sol[k]);
+    if (c->ev_clamp[k]) cudaEventDestroy(c->ev_clamp[k]);
+  }
   if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -357,14 +368,12 @@ extern "C" int rdc_assemble(rdc_ctx* c, double time, double dt) {
   if (!c->have_params) { c->err = "rdc_assemble: rdc_set_params has not been called"; return RDC_E_STATE; }
   if (!(dt > 0.0)) { c->err = "rdc_assemble: dt must be positive"; return RDC_E_ARG; }
   c->time = time; c->dt = dt;
-  cudaEventRecord(c->ev0, c->stream);
+  // no host synchronisation here: the elapsed time is read when the statistics are asked for
+  cudaEventRecord(c->ev_asm[0], c->stream);
   int rc = launch_assemble(c);
   if (rc) return rc;
-  cudaEventRecord(c->ev1, c->stream);
-  RDC_CUDA(cudaEventSynchronize(c->ev1));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-  c->st.ms_assemble = ms;
+  cudaEventRecord(c->ev_asm[1], c->stream);
+  c->t_asm_pending = true;
   c->assembled = true;
   return RDC_OK;
 }
@@ -375,13 +384,10 @@ extern "C" int rdc_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, i
   int its = 0;
   double res = 0;
   c->st.n_spmv = 0;
-  cudaEventRecord(c->ev0, c->stream);
+  cudaEventRecord(c->ev_sol[0], c->stream);
   int rc = solver_solve(c, ksp, pc, rtol, maxits, restart, &its, &res);
-  cudaEventRecord(c->ev1, c->stream);
-  cudaEventSynchronize(c->ev1);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-  c->st.ms_solve = ms;
+  cudaEventRecord(c->ev_sol[1], c->stream);
+  c->t_sol_pending = true;
   c->st.iterations = its;
   c->st.resnorm = res;
   if (iterations) *iterations = its;
@@ -395,14 +401,11 @@ extern "C" int rdc_clamp(rdc_ctx* c) {
     if (!c->have_params || !c->d_rt) { c->err = "rdc_clamp (RIPF): parameters and RT dose field are required"; return RDC_E_STATE; }
     if (!(c->dt > 0.0)) { c->err = "rdc_clamp (RIPF): time step unknown; call rdc_assemble/rdc_step or rdc_set_dt first"; return RDC_E_STATE; }
   }
-  cudaEventRecord(c->ev0, c->stream);
+  cudaEventRecord(c->ev_clamp[0], c->stream);
   int rc = launch_clamp(c);
   if (rc) return rc;
-  cudaEventRecord(c->ev1, c->stream);
-  cudaEventSynchronize(c->ev1);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-  c->st.ms_clamp = ms;
+  cudaEventRecord(c->ev_clamp[1], c->stream);
+  c->t_clamp_pending = true;
   return RDC_OK;
 }
 
@@ -457,6 +460,17 @@ extern "C" int rdc_bench_spmv(rdc_ctx* c, int reps, double* mean_ms) {
 
 extern "C" int rdc_get_stats(rdc_ctx* c, struct rdc_stats* s) {
   if (!c || !s) return RDC_E_ARG;
+  cudaSetDevice(c->device);
+  auto resolve = [&](bool& pending, cudaEvent_t* ev, double& out) {
+    if (!pending) return;
+    float ms = 0;
+    if (cudaEventSynchronize(ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) out = ms;
+    pending = false;
+  };
+  resolve(c->t_asm_pending, c->ev_asm, c->st.ms_assemble);
+  resolve(c->t_sol_pending, c->ev_sol, c->st.ms_solve);
+  resolve(c->t_clamp_pending, c->ev_clamp, c->st.ms_clamp);
+  solver_spmv_time(c);
   *s = c->st;
   return RDC_OK;
 }
@@ -467,9 +481,11 @@ extern "C" int rdc_download_csr(rdc_ctx* c, int64_t* n_rows, int64_t* nnz, int64
   CHECK_CTX(c);
   if (!c->assembled) { c->err = "rdc_download_csr: nothing assembled"; return RDC_E_STATE; }
   const HostSetup& S = c->S;
-  const int nv = c->nv, vv = nv * nv;
+  const int nv = c->nv, vv = nv * nv, nkv = c->nkv;
   const int32_t no = S.n_owned;
-  std::vector<double> hval((size_t)c->nnzb * vv), hrhs((size_t)no * nv);
+  int plane[25];  // entry (a,b) -> stored plane, -1 = structural zero (kept explicit in the reference's AIJ pattern)
+  for (int ab = 0, s = 0; ab < vv; ab++) plane[ab] = (c->kmask >> ab & 1u) ? s++ : -1;
+  std::vector<double> hval((size_t)c->nnzb * nkv), hrhs((size_t)no * nv);
   RDC_CUDA(cudaMemcpyAsync(hval.data(), c->d_val, hval.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaMemcpyAsync(hrhs.data(), c->d_rhs, hrhs.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
@@ -501,7 +517,8 @@ extern "C" int rdc_download_csr(rdc_ctx* c, int64_t* n_rows, int64_t* nnz, int64
       for (const auto& ck : cols)
         for (int b = 0; b < nv; b++, p++) {
           o_col[p] = ck.first + b;
-          o_val[p] = hval[(size_t)r0 * vv + (size_t)(a * nv + b) * L + ck.second];
+          const int pl = plane[a * nv + b];
+          o_val[p] = pl < 0 ? 0.0 : hval[(size_t)r0 * nkv + (size_t)pl * L + ck.second];
         }
       o_ptr[r + 1] = p;
     }

@@ -13,8 +13,10 @@
 //   * phase 2: one thread per block of the CTA's rows sums the staged contributions in the fixed order of
 //     a precomputed contributor list (ascending element id == the reference's serial loop order) and
 //     writes every value of K exactly once, coalesced.  No float atomics; bit-reproducible.
-// Operator layout ("row-local SoA"): block row i has L_i blocks; entry (a,b) of block k of row i lives at
-//   val[rowptr[i]*v*v + (a*v+b)*L_i + k]   so that a half-warp reading one row is fully coalesced.
+// Operator layout ("row-local SoA"): block row i has L_i blocks; only the NKV structurally non-zero entries
+// (a,b) of the model's v x v node block are stored (KMASK); entry plane s = rank of bit a*v+b in KMASK:
+//   val[rowptr[i]*NKV + s*L_i + k]   so that a half-warp reading one row is fully coalesced.
+// The CTA that finishes the diagonal block of a row also writes the point-Jacobi scaling 1/K_ii.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -45,8 +47,10 @@ struct AsmArgs {
   const int32_t* cta_node;
   const int32_t* cptr;
   const uint16_t* clist;
+  const int32_t* diag_blk;
   double* val;
   double* rhs;
+  double* dinv;
 };
 
 __host__ __device__ constexpr int popc(unsigned m) { int c = 0; while (m) { c += m & 1u; m >>= 1; } return c; }
@@ -129,6 +133,7 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   double* stageF = smem + (size_t)NEN * NKV * PAIRS;  // [NV][PAIRS]
   __shared__ int s_rowptr[PAIRS + 1];
   __shared__ int s_n2e[PAIRS + 1];
+  __shared__ int s_diag[PAIRS];
   __shared__ int s_cptr[PAIRS * NEN + 1];            // contributor offsets of the CTA's blocks (relative)
   __shared__ unsigned short s_clist[PAIRS * NEN];    // contributor codes j*PAIRS + pair = offset inside a stage slot
 
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   const int blk0 = d1.x, nblk = d1.y;
   // index prologue: everything phase 2 needs goes to shared memory now, so its loads overlap phase 1
   for (int r = tid; r <= nnode; r += PAIRS) { s_rowptr[r] = A.rowptr[node0 + r]; s_n2e[r] = A.n2e_ptr[node0 + r] - pair0; }
+  for (int r = tid; r < nnode; r += PAIRS) s_diag[r] = A.diag_blk[node0 + r];
   {
     const int c_base = d1.z;
     for (int b = tid; b <= nblk; b += PAIRS) s_cptr[b] = A.cptr[blk0 + b] - c_base;
@@ -378,9 +384,13 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
 #pragma unroll
       for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * NEN * PAIRS];
     }
-    double* dst = A.val + (size_t)r0 * VV + kk;
+    double* dst = A.val + (size_t)r0 * NKV + kk;
 #pragma unroll
-    for (int ab = 0; ab < VV; ab++) dst[(size_t)ab * L] = (KMASK >> ab & 1u) ? acc[slot_of(KMASK, ab)] : 0.0;
+    for (int s = 0; s < NKV; s++) dst[(size_t)s * L] = acc[s];
+    if (B == s_diag[lo]) {  // point Jacobi: every model has C[a][a] in its mask
+#pragma unroll
+      for (int a = 0; a < NV; a++) A.dinv[(size_t)(node0 + lo) * NV + a] = 1.0 / acc[slot_of(KMASK, a * NV + a)];
+    }
   }
   for (int t = tid; t < nnode * NV; t += PAIRS) {
     const int r = t / NV, a = t - r * NV;
@@ -389,15 +399,6 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
     for (int q = q0; q < q1; q++) f += stageF[a * PAIRS + q];
     A.rhs[(size_t)(node0 + r) * NV + a] = f;
   }
-}
-
-// diagonal of K -> dinv (point Jacobi) ; one thread per owned node
-__global__ void k_extract_diag(int n_owned, int nv, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ diag_blk,
-                               const double* __restrict__ val, double* __restrict__ dinv) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_owned) return;
-  const int r0 = rowptr[i], L = rowptr[i + 1] - r0, k = diag_blk[i] - r0;
-  for (int a = 0; a < nv; a++) dinv[(size_t)i * nv + a] = 1.0 / val[(size_t)r0 * nv * nv + (size_t)(a * nv + a) * L + k];
 }
 
 // ---------------------------------------------------------------------------------- host launchers
@@ -452,8 +453,8 @@ int pairs_per_cta_for(int model, int etype) {
   const bool v5 = (model == RDC_PIHNA || model == RDC_PROTEAS);
   if (etype == RDC_TET4) {
     if (v5) return 128;
-    const char* e = getenv("RDC_ASM_PAIRS");  // tuning knob: 128 or 256 pairs per CTA for the 3-variable models
-    return (e && atoi(e) == 128) ? 128 : 256;
+    const char* e = getenv("RDC_ASM_PAIRS");  // tuning knob: 128 (default, 4 CTAs/SM) or 256 pairs per CTA
+    return (e && atoi(e) == 256) ? 256 : 128;
   }
   return 128;
 }
@@ -463,7 +464,7 @@ int launch_assemble(rdc_ctx* c) {
   A.conn = c->d_conn; A.xyz4 = c->d_xyz; A.u_old = c->d_uold; A.efield = c->d_efield;
   A.aux0 = nullptr; A.aux1 = nullptr;
   A.n2e_ptr = c->d_n2e_ptr; A.pair = c->d_pair; A.rowptr = c->d_rowptr; A.cta_node = c->d_cta_node;
-  A.cptr = c->d_cptr; A.clist = c->d_clist; A.val = c->d_val; A.rhs = c->d_rhs;
+  A.cptr = c->d_cptr; A.clist = c->d_clist; A.diag_blk = c->d_diag_blk; A.val = c->d_val; A.rhs = c->d_rhs; A.dinv = c->d_dinv;
   const double* p = c->params.data();
   const double h = c->dt / 2.0;
   switch (c->model) {
@@ -544,11 +545,14 @@ int launch_assemble(rdc_ctx* c) {
   return RDC_E_ARG;
 }
 
-int launch_extract_diag(rdc_ctx* c) {
-  const int n = c->S.n_owned;
-  k_extract_diag<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->nv, c->d_rowptr, c->d_diag_blk, c->d_val, c->d_dinv);
-  c->st.kernel_launches++;
-  RDC_CUDA(cudaGetLastError());
+unsigned model_kmask(int model) {
+  switch (model) {
+    case RDC_ADPM: return Adpm::CMASK | Adpm::SMASK | Adpm::TMASK;
+    case RDC_PIHNA: return Pihna::CMASK | Pihna::SMASK | Pihna::TMASK;
+    case RDC_RIPF: return Ripf::CMASK | Ripf::SMASK | Ripf::TMASK;
+    case RDC_PROTEAS: return Proteas::CMASK | Proteas::SMASK | Proteas::TMASK;
+    case RDC_HCC: return Hcc::CMASK | Hcc::SMASK | Hcc::TMASK;
+  }
   return 0;
 }
 

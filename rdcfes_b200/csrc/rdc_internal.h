@@ -83,6 +83,11 @@ struct rdc_ctx {
   int32_t* d_dofmap = nullptr;       // [n_loc*nv] global dof id of each local dof (gather/scatter of user vectors)
   int ncta = 0;
   int64_t nnzb = 0;
+  // structurally non-zero entries (a,b) of the model's v x v node block (bit a*nv+b).  Only these NKV entry
+  // planes are stored, assembled and streamed by SpMV; rdc_download_csr re-inserts the explicit zeros the
+  // reference keeps in its AIJ pattern.
+  unsigned kmask = 0;
+  int nkv = 0;
 
   // device: operator and vectors.  Vectors are [n_loc*nv]: owned part first, ghost part after it.
   double *d_val = nullptr, *d_rhs = nullptr, *d_dinv = nullptr;
@@ -107,14 +112,16 @@ struct rdc_ctx {
 
   // stats
   rdc_stats st = {};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;          // scratch pair (rdc_bench_spmv)
+  cudaEvent_t ev_asm[2] = {nullptr, nullptr}, ev_sol[2] = {nullptr, nullptr}, ev_clamp[2] = {nullptr, nullptr};
+  bool t_asm_pending = false, t_sol_pending = false, t_clamp_pending = false;  // elapsed times are read lazily
   std::string err;
 };
 
 namespace rdc {
 // assemble.cu
-int launch_assemble(rdc_ctx* c);
-int launch_extract_diag(rdc_ctx* c);
+int launch_assemble(rdc_ctx* c);   // K, F and the point-Jacobi scaling dinv = 1/diag(K)
+unsigned model_kmask(int model);
 int upload_fe_tables();
 // solver.cu
 int solver_init(rdc_ctx* c);
@@ -122,6 +129,8 @@ void solver_free(rdc_ctx* c);
 int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int restart, int* its, double* res);
 int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done = false);
 int launch_clamp(rdc_ctx* c);
+void solver_spmv_time(rdc_ctx* c);   // resolves the lazily summed SpMV event times into st.ms_spmv_total
+int spmv_masks_ok();                // solver.cu's entry masks agree with the model definitions
 int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc);     // dst_loc[l] = src[dofmap[l]]
 int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob);    // owned part only
 int halo_exchange(rdc_ctx* c, double* x);                                   // fills the ghost part of x

@@ -23,6 +23,8 @@ namespace rdc {
 static constexpr int RED_BLOCKS = 592;   // 4 CTAs per SM on 148 SMs
 static constexpr int RED_THREADS = 256;
 static constexpr int MD_CHUNK = 8;       // vectors per multi-dot pass
+static constexpr int SPMV_SUB = 1024;    // rows whose row pointers one SpMV CTA stages in shared memory at a time
+static constexpr int SPMV_MAX_GRID = 148 * 32;
 
 }  // namespace rdc
 
@@ -47,115 +49,15 @@ struct SolverWork {
   static constexpr int MAX_EV = 512;
   cudaEvent_t ev[2 * MAX_EV];
   int n_ev_used = 0;
+  bool spmv_time_pending = false;
+  static constexpr int RING = 8;
+  cudaEvent_t ev_ring[RING];
+  int* h_ring = nullptr;     // pinned copies of the convergence flag
+  int4* tiles = nullptr;     // SpMV tiles {row0, nrows, first block, nblocks} (k_spmv_tma)
+  int n_tiles = 0;
 };
 
 namespace rdc {
-
-// ------------------------------------------------------------------------------------------ SpMV
-// G lanes per block row; lane k owns blocks k, k+G, ... of the row (row-local SoA layout -> every load of a
-// lane group is one contiguous segment).  The operator is streamed once (read-only, no L1 allocation) while
-// the gathered x stays cacheable.  rowscale != nullptr fuses the Jacobi scaling: y = D^-1 (A x).
-__device__ __forceinline__ double ld_stream(const double* p) {
-  double v;
-  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ int ld_stream_i32(const int* p) {
-  int v;
-  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
-
-template <int NV, int G, int R>
-__global__ void __launch_bounds__(256, (NV == 3 && R == 1) ? 8 : 1) k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                              const double* __restrict__ val, const double* __restrict__ x,
-                                              double* __restrict__ y, const double* __restrict__ rowscale,
-                                              const int* __restrict__ done) {
-  if (done && *done) return;
-  const int lane = threadIdx.x & (G - 1);
-  const int grp = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) / G);
-  // R consecutive rows per lane group: the loads of all R rows are issued before any is consumed
-  int r0[R], L[R];
-#pragma unroll
-  for (int q = 0; q < R; q++) {
-    const int row = grp * R + q;
-    r0[q] = row < n_rows ? rowptr[row] : 0;
-    L[q] = row < n_rows ? rowptr[row + 1] - r0[q] : 0;
-  }
-  double acc[R][NV];
-#pragma unroll
-  for (int q = 0; q < R; q++)
-#pragma unroll
-    for (int a = 0; a < NV; a++) acc[q][a] = 0.0;
-  int kmax = 0;
-#pragma unroll
-  for (int q = 0; q < R; q++) kmax = max(kmax, L[q]);
-  for (int k = lane; k < kmax; k += G) {
-    int c[R];
-    double a_[R][NV * NV];
-#pragma unroll
-    for (int q = 0; q < R; q++) {
-      const bool on = k < L[q];
-      c[q] = on ? ld_stream_i32(col + r0[q] + k) : 0;
-      const double* v0 = val + (size_t)r0[q] * (NV * NV);
-#pragma unroll
-      for (int e = 0; e < NV * NV; e++) a_[q][e] = on ? ld_stream(v0 + (size_t)e * L[q] + k) : 0.0;
-    }
-#pragma unroll
-    for (int q = 0; q < R; q++) {
-      double xv[NV];
-#pragma unroll
-      for (int b = 0; b < NV; b++) xv[b] = x[(size_t)c[q] * NV + b];
-#pragma unroll
-      for (int a = 0; a < NV; a++)
-#pragma unroll
-        for (int b = 0; b < NV; b++) acc[q][a] = fma(a_[q][a * NV + b], xv[b], acc[q][a]);
-    }
-  }
-#pragma unroll
-  for (int off = G / 2; off > 0; off >>= 1)
-#pragma unroll
-    for (int q = 0; q < R; q++)
-#pragma unroll
-      for (int a = 0; a < NV; a++) acc[q][a] += __shfl_xor_sync(0xffffffffu, acc[q][a], off, G);
-  if (lane == 0) {
-#pragma unroll
-    for (int q = 0; q < R; q++) {
-      const int row = grp * R + q;
-      if (row < n_rows) {
-#pragma unroll
-        for (int a = 0; a < NV; a++) {
-          const size_t o = (size_t)row * NV + a;
-          y[o] = rowscale ? acc[q][a] * rowscale[o] : acc[q][a];
-        }
-      }
-    }
-  }
-}
-
-int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done) {
-  const int n = c->S.n_owned;
-  const int* done = (check_done && c->work) ? c->work->state : nullptr;
-  static int R = -1;
-  if (R < 0) { const char* e = getenv("RDC_SPMV_R"); R = e ? atoi(e) : 1; if (R != 1 && R != 2 && R != 4) R = 1; }
-  constexpr int G = 16;
-  const size_t ngroups = ((size_t)n + R - 1) / R;
-  const unsigned grid = (unsigned)((ngroups * G + 255) / 256);
-  // every SpMV launch of a solve is bracketed by its own event pair (summed after the solve) so that the
-  // roofline of the dominant kernel is measured live, inside the timed step
-  SolverWork* W = c->work;
-  const bool timed = check_done && W && W->n_ev_used < SolverWork::MAX_EV;
-  if (timed) cudaEventRecord(W->ev[2 * W->n_ev_used], c->stream);
-#define RDC_SPMV_LAUNCH(NVV, RR) k_spmv<NVV, G, RR><<<grid, 256, 0, c->stream>>>(n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, done)
-  if (c->nv == 3) { if (R == 1) RDC_SPMV_LAUNCH(3, 1); else if (R == 2) RDC_SPMV_LAUNCH(3, 2); else RDC_SPMV_LAUNCH(3, 4); }
-  else { if (R == 1) RDC_SPMV_LAUNCH(5, 1); else RDC_SPMV_LAUNCH(5, 2); }
-#undef RDC_SPMV_LAUNCH
-  if (timed) { cudaEventRecord(W->ev[2 * W->n_ev_used + 1], c->stream); W->n_ev_used++; }
-  c->st.kernel_launches++;
-  c->st.n_spmv++;
-  RDC_CUDA(cudaGetLastError());
-  return 0;
-}
 
 // ------------------------------------------------------------------------- reductions (fixed order)
 __device__ __forceinline__ double warp_sum(double v) {
@@ -164,8 +66,9 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// block-reduce NV values, write partial[blockIdx][k]; the last block to finish adds the partials of all
-// blocks in index order and writes out[k] -- one launch, deterministic.
+// Block-reduce NVAL values into partial[k * gridDim.x + blockIdx.x]; the last block to finish adds the partials
+// of all blocks -- thread t takes blocks t, t+256, ... in order, then a fixed shuffle/shared-memory tree -- and
+// writes out[k].  One launch, no float atomics, bit-reproducible for a fixed grid size.
 template <int NVAL>
 __device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double* partial, unsigned* counter, double* out) {
   __shared__ double s_red[RED_THREADS / 32][NVAL];
@@ -181,7 +84,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double*
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < RED_THREADS / 32; w++) s += s_red[w][threadIdx.x];
-    partial[(size_t)blockIdx.x * NVAL + threadIdx.x] = s;
+    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
   }
   __threadfence();
   __syncthreads();
@@ -189,13 +92,447 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double*
   __syncthreads();
   if (s_last) {
     __threadfence();
-    if (threadIdx.x < NVAL && threadIdx.x < nval) {
+#pragma unroll
+    for (int k = 0; k < NVAL; k++) {
+      if (k >= nval) break;
       double s = 0.0;
-      for (unsigned b = 0; b < gridDim.x; b++) s += partial[(size_t)b * NVAL + threadIdx.x];
-      out[threadIdx.x] = s;
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += RED_THREADS) s += __ldcg(partial + (size_t)k * gridDim.x + b);
+      s = warp_sum(s);
+      __syncthreads();
+      if (lane == 0) s_red[wid][0] = s;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < RED_THREADS / 32; w++) t += s_red[w][0];
+        out[k] = t;
+      }
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
+}
+
+// ------------------------------------------------------------------------------------------ SpMV
+// Half-warp per block row, lane k owns blocks k, k+16, ... of the row (row-local SoA layout -> every load of a
+// half-warp is one contiguous segment).  Only the NKV structurally non-zero entry planes of the model are
+// stored and streamed (KMASK).  The operator is read once (read-only, no L1 allocation) while the gathered x
+// stays cacheable.  A fixed-size grid walks the rows, so the fused dot products of the Krylov methods reduce
+// over a bounded number of per-CTA partials in a fixed order:
+//   PLAIN    y = S (A x)                       (S = rowscale or identity)
+//   DOT_W    y = S (A x) ; out = { <w, y> }                                   BiCGStab  v = B A p, <r0, v>
+//   DOT_SELF y = S (A x) ; out = { <x, y>, <y, y> }                           BiCGStab  t = B A s, <s,t>, <t,t>
+//   RESID    y = y2 = S (w - A x) ; out = { <y, y>, <S w, S w> }              initial residual and ||B b||^2
+enum { SPMV_PLAIN = 0, SPMV_DOT_W = 1, SPMV_DOT_SELF = 2, SPMV_RESID = 3 };
+
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_i32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__host__ __device__ constexpr int popc_c(unsigned m) { int c = 0; while (m) { c += m & 1u; m >>= 1; } return c; }
+__host__ __device__ constexpr int slot_c(unsigned mask, int bitpos) { return popc_c(mask & ((1u << bitpos) - 1u)); }
+
+template <int NV, unsigned KMASK, int MODE, int MINB>
+__global__ void __launch_bounds__(RED_THREADS, MINB)
+k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+       const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ rowscale,
+       const double* __restrict__ w, double* __restrict__ y2, double* partial, unsigned* counter, double* out,
+       const int* __restrict__ done) {
+  if (done && *done) return;
+  constexpr int G = 16;
+  constexpr int NKV = popc_c(KMASK);
+  constexpr int HW = RED_THREADS / G;     // half-warps (rows in flight) per CTA
+  const int lane = threadIdx.x & (G - 1), hw = threadIdx.x / G;
+  double d[2] = {0.0, 0.0};
+  // Rows are dealt to the half-warps of the whole grid round-robin, so at any time the grid streams one moving
+  // window of the operator (sequential DRAM pages; a contiguous chunk per CTA measured 12 % slower).
+  // The kernel is bound by the latency of the per-row dependency chain, so everything that does not depend on
+  // the row's dot products is issued ahead of it (EARLY): the row pointers of the next trip and the epilogue
+  // operands (Jacobi scale, the dot partner).  Chain left: operator/column loads -> x gather -> FMA -> store.
+  constexpr bool EARLY = MINB != 8;
+  const int stride = (int)gridDim.x * HW;
+  int row = (int)blockIdx.x * HW + hw;
+  int r0n = 0, r1n = 0;
+  if (EARLY && row < n_rows) { r0n = rowptr[row]; r1n = rowptr[row + 1]; }
+#pragma unroll 1
+  for (; row < n_rows; row += stride) {
+    int r0, L;
+    if (EARLY) {
+      r0 = r0n; L = r1n - r0n;
+      if (row + stride < n_rows) { r0n = rowptr[row + stride]; r1n = rowptr[row + stride + 1]; }
+    } else {
+      r0 = rowptr[row];
+      L = rowptr[row + 1] - r0;
+    }
+    const size_t o = (size_t)row * NV + (lane < NV ? lane : 0);
+    double sc = 1.0, wv = 0.0;
+    if (EARLY && lane < NV) {
+      if (rowscale) sc = rowscale[o];
+      if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
+      if (MODE == SPMV_DOT_SELF) wv = x[o];
+    }
+    double acc[NV];
+#pragma unroll
+    for (int a = 0; a < NV; a++) acc[a] = 0.0;
+    // the 16 lanes of a half-warp always run the same trips, so the half-warp mask is exact
+    const unsigned hmask = 0xffffu << (threadIdx.x & 16);
+#pragma unroll 1
+    for (int k = lane; k < L; k += G) {
+      const int c = ld_stream_i32(col + r0 + k);
+      const double* v0 = val + (size_t)r0 * NKV + k;
+      double a_[NKV];
+#pragma unroll
+      for (int e = 0; e < NKV; e++) a_[e] = ld_stream(v0 + (size_t)e * L);
+      double xv[NV];
+#pragma unroll
+      for (int b = 0; b < NV; b++) xv[b] = x[(size_t)c * NV + b];
+#pragma unroll
+      for (int ab = 0; ab < NV * NV; ab++)
+        if (KMASK >> ab & 1u) acc[ab / NV] = fma(a_[slot_c(KMASK, ab)], xv[ab % NV], acc[ab / NV]);
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+      for (int a = 0; a < NV; a++) acc[a] += __shfl_xor_sync(hmask, acc[a], off, G);
+    // lanes 0..NV-1 finish one component each (consecutive addresses)
+    if (lane < NV) {
+      double mine = acc[0];
+#pragma unroll
+      for (int a = 1; a < NV; a++)
+        if (lane == a) mine = acc[a];
+      if (!EARLY) {
+        if (rowscale) sc = rowscale[o];
+        if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
+        if (MODE == SPMV_DOT_SELF) wv = x[o];
+      }
+      if (MODE == SPMV_PLAIN) {
+        y[o] = mine * sc;
+      } else if (MODE == SPMV_DOT_W) {
+        const double yv = mine * sc;
+        y[o] = yv;
+        d[0] = fma(wv, yv, d[0]);
+      } else if (MODE == SPMV_DOT_SELF) {
+        const double yv = mine * sc;
+        y[o] = yv;
+        d[0] = fma(wv, yv, d[0]);
+        d[1] = fma(yv, yv, d[1]);
+      } else {
+        const double yv = (wv - mine) * sc;
+        y[o] = yv;
+        if (y2) y2[o] = yv;
+        d[0] = fma(yv, yv, d[0]);
+        d[1] = fma(wv * sc, wv * sc, d[1]);
+      }
+    }
+  }
+  if (MODE != SPMV_PLAIN) grid_reduce<2>(d, MODE == SPMV_DOT_W ? 1 : 2, partial, counter, out);
+}
+
+// ---- TMA-staged variant (the default) ------------------------------------------------------------------------
+// The LDG kernel above keeps the streamed operator in registers while it is in flight, and ptxas recycles those
+// registers between the FMAs, so only 2-3 of the NKV+1 loads of a thread are outstanding (SASS, ncu: long-scoreboard
+// bound at ~52 % DRAM throughput with 100 % occupancy).  Here the stream never touches registers: 16 consecutive
+// block rows are one contiguous record of the row-local SoA operator, so ONE elected thread moves a whole tile
+// (operator values, column ids, row pointers) with three 1-D bulk copies (cp.async.bulk -> UBLKCP) into a ring of
+// shared-memory stages, completion counted by an mbarrier.  STAGES-1 tiles per CTA are always in flight
+// (~15 KB per CTA and stage), the half-warps compute from shared memory and only gather x through L1/L2.
+// What bounds it now is the number of rows whose x gathers are in flight per SM (threads), not the stream:
+// 2 stages x 6 CTAs/SM (96 rows) measured 0.334 ms, 3 stages x 4 CTAs/SM (64 rows) 0.397 ms on the headline case.
+// Tiles are cut on the host (<= 16 rows, <= SPMV_CAPB blocks): {row0, nrows, first block, nblocks}.
+static constexpr int SPMV_CAPB = 256;
+static constexpr int SPMV_TILE_ROWS = 16;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int NKV>
+struct SpmvStage {
+  static constexpr int VAL_BYTES = ((SPMV_CAPB * NKV + 2) * 8 + 15) / 16 * 16;
+  static constexpr int COL_BYTES = ((SPMV_CAPB + 4) * 4 + 15) / 16 * 16;
+  static constexpr int RP_BYTES = ((SPMV_TILE_ROWS + 1 + 4) * 4 + 15) / 16 * 16;
+  static constexpr int BYTES = (VAL_BYTES + COL_BYTES + RP_BYTES + 127) / 128 * 128;
+};
+
+template <int NV, unsigned KMASK, int MODE, int STAGES>
+__global__ void __launch_bounds__(RED_THREADS)
+k_spmv_tma(int n_tiles, const int4* __restrict__ tiles, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+           const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
+           const double* __restrict__ rowscale, const double* __restrict__ w, double* __restrict__ y2, double* partial,
+           unsigned* counter, double* out, const int* __restrict__ done) {
+  if (done && *done) return;
+  constexpr int G = 16;
+  constexpr int NKV = popc_c(KMASK);
+  typedef SpmvStage<NKV> ST;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[STAGES];
+  const int tid = threadIdx.x, lane = tid & (G - 1), hw = tid / G;
+  const unsigned hmask = 0xffffu << (tid & 16);
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(smem_u32(&s_bar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer side (thread 0): three bulk copies per tile, sources aligned down to 16 B
+  auto issue = [&](int tile, int stage) {
+    const int4 t = tiles[tile];                       // {row0, nrows, b0, nblk}
+    const int skip_v = (int)(((long long)t.z * NKV) & 1), skip_c = t.z & 3, skip_r = t.x & 3;
+    const unsigned vb = (unsigned)(((skip_v + t.w * NKV) * 8 + 15) & ~15);
+    const unsigned cb = (unsigned)(((skip_c + t.w) * 4 + 15) & ~15);
+    const unsigned rb = (unsigned)(((skip_r + t.y + 1) * 4 + 15) & ~15);
+    unsigned char* base = s_raw + (size_t)stage * ST::BYTES;
+    const unsigned bar = smem_u32(&s_bar[stage]);
+    mbar_expect_tx(bar, vb + cb + rb);
+    bulk_g2s(smem_u32(base), val + ((long long)t.z * NKV - skip_v), vb, bar);
+    bulk_g2s(smem_u32(base + ST::VAL_BYTES), col + (t.z - skip_c), cb, bar);
+    bulk_g2s(smem_u32(base + ST::VAL_BYTES + ST::COL_BYTES), rowptr + (t.x - skip_r), rb, bar);
+  };
+  const int first = (int)blockIdx.x, tstride = (int)gridDim.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES - 1; s++)
+      if (first + s * tstride < n_tiles) issue(first + s * tstride, s);
+  }
+  double d[2] = {0.0, 0.0};
+  int4 tn = first < n_tiles ? tiles[first] : make_int4(0, 0, 0, 0);
+#pragma unroll 1
+  for (int i = 0, tile = first; tile < n_tiles; i++, tile += tstride) {
+    const int stage = i % STAGES;
+    const int4 t = tn;
+    if (tile + tstride < n_tiles) tn = tiles[tile + tstride];
+    // refill the stage that was consumed in the previous iteration (every thread has passed its barrier)
+    if (tid == 0 && tile + (STAGES - 1) * tstride < n_tiles) issue(tile + (STAGES - 1) * tstride, (i + STAGES - 1) % STAGES);
+    // epilogue operands do not depend on the tile data: fetch them while the tile is (possibly) still landing
+    const bool live = hw < t.y;
+    const int row = t.x + hw;
+    const size_t o = (size_t)row * NV + (lane < NV ? lane : 0);
+    double sc = 1.0, wv = 0.0;
+    if (live && lane < NV) {
+      if (rowscale) sc = rowscale[o];
+      if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
+      if (MODE == SPMV_DOT_SELF) wv = x[o];
+    }
+    mbar_wait(smem_u32(&s_bar[stage]), (unsigned)((i / STAGES) & 1));
+    if (live) {
+      const unsigned char* base = s_raw + (size_t)stage * ST::BYTES;
+      const double* s_val = reinterpret_cast<const double*>(base) + (((long long)t.z * NKV) & 1);
+      const int* s_col = reinterpret_cast<const int*>(base + ST::VAL_BYTES) + (t.z & 3);
+      const int* s_rp = reinterpret_cast<const int*>(base + ST::VAL_BYTES + ST::COL_BYTES) + (t.x & 3);
+      const int r0 = s_rp[hw] - t.z;                 // block offset inside the tile
+      const int L = s_rp[hw + 1] - s_rp[hw];
+      double acc[NV];
+#pragma unroll
+      for (int a = 0; a < NV; a++) acc[a] = 0.0;
+#pragma unroll 1
+      for (int k = lane; k < L; k += G) {
+        const int c = s_col[r0 + k];
+        double xv[NV];
+#pragma unroll
+        for (int b = 0; b < NV; b++) xv[b] = x[(size_t)c * NV + b];
+        const double* v0 = s_val + (size_t)r0 * NKV + k;
+#pragma unroll
+        for (int ab = 0; ab < NV * NV; ab++)
+          if (KMASK >> ab & 1u) acc[ab / NV] = fma(v0[slot_c(KMASK, ab) * L], xv[ab % NV], acc[ab / NV]);
+      }
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+        for (int a = 0; a < NV; a++) acc[a] += __shfl_xor_sync(hmask, acc[a], off, G);
+      if (lane < NV) {
+        double mine = acc[0];
+#pragma unroll
+        for (int a = 1; a < NV; a++)
+          if (lane == a) mine = acc[a];
+        if (MODE == SPMV_PLAIN) {
+          y[o] = mine * sc;
+        } else if (MODE == SPMV_DOT_W) {
+          const double yv = mine * sc;
+          y[o] = yv;
+          d[0] = fma(wv, yv, d[0]);
+        } else if (MODE == SPMV_DOT_SELF) {
+          const double yv = mine * sc;
+          y[o] = yv;
+          d[0] = fma(wv, yv, d[0]);
+          d[1] = fma(yv, yv, d[1]);
+        } else {
+          const double yv = (wv - mine) * sc;
+          y[o] = yv;
+          if (y2) y2[o] = yv;
+          d[0] = fma(yv, yv, d[0]);
+          d[1] = fma(wv * sc, wv * sc, d[1]);
+        }
+      }
+    }
+    __syncthreads();   // the stage may be refilled from the next iteration on
+  }
+  if (MODE != SPMV_PLAIN) grid_reduce<2>(d, MODE == SPMV_DOT_W ? 1 : 2, partial, counter, out);
+}
+
+static int spmv_grid(int n_rows, int nv) {
+  static int per_sm = -1;
+  if (per_sm < 0) { const char* e = getenv("RDC_SPMV_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; }
+  const int want = (n_rows + 15) / 16;
+  int cap = 148 * (per_sm > 0 ? per_sm : (nv == 3 ? 4 : 3));
+  if (cap > SPMV_MAX_GRID) cap = SPMV_MAX_GRID;   // bounded number of per-CTA partials for the fused dots
+  return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+template <int NV, unsigned KMASK>
+static void spmv_mode(int mode, unsigned grid, cudaStream_t st, int n, const int32_t* rowptr, const int32_t* col, const double* val,
+                      const double* x, double* y, const double* rowscale, const double* w, double* y2, double* partial,
+                      unsigned* counter, double* out, const int* done) {
+  static int minb = -1;  // tuning knob (3-variable models): resident CTAs per SM the kernel is compiled for
+  if (minb < 0) { const char* e = getenv("RDC_SPMV_MINB"); minb = e ? atoi(e) : 4; }
+#define RDC_SPMV_GO(MODE, MB) k_spmv<NV, KMASK, MODE, MB><<<grid, RED_THREADS, 0, st>>>(n, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done)
+  if (NV == 3 && minb == 4) {
+    switch (mode) {
+      case SPMV_PLAIN: RDC_SPMV_GO(SPMV_PLAIN, (NV == 3 ? 4 : 3)); break;
+      case SPMV_DOT_W: RDC_SPMV_GO(SPMV_DOT_W, (NV == 3 ? 4 : 3)); break;
+      case SPMV_DOT_SELF: RDC_SPMV_GO(SPMV_DOT_SELF, (NV == 3 ? 4 : 3)); break;
+      default: RDC_SPMV_GO(SPMV_RESID, (NV == 3 ? 4 : 3)); break;
+    }
+    return;
+  }
+  if (NV == 3 && minb == 5) {
+    switch (mode) {
+      case SPMV_PLAIN: RDC_SPMV_GO(SPMV_PLAIN, (NV == 3 ? 5 : 3)); break;
+      case SPMV_DOT_W: RDC_SPMV_GO(SPMV_DOT_W, (NV == 3 ? 5 : 3)); break;
+      case SPMV_DOT_SELF: RDC_SPMV_GO(SPMV_DOT_SELF, (NV == 3 ? 5 : 3)); break;
+      default: RDC_SPMV_GO(SPMV_RESID, (NV == 3 ? 5 : 3)); break;
+    }
+    return;
+  }
+  if (NV == 3 && minb == 6) {
+    switch (mode) {
+      case SPMV_PLAIN: RDC_SPMV_GO(SPMV_PLAIN, (NV == 3 ? 6 : 3)); break;
+      case SPMV_DOT_W: RDC_SPMV_GO(SPMV_DOT_W, (NV == 3 ? 6 : 3)); break;
+      case SPMV_DOT_SELF: RDC_SPMV_GO(SPMV_DOT_SELF, (NV == 3 ? 6 : 3)); break;
+      default: RDC_SPMV_GO(SPMV_RESID, (NV == 3 ? 6 : 3)); break;
+    }
+    return;
+  }
+  switch (mode) {
+    case SPMV_PLAIN: RDC_SPMV_GO(SPMV_PLAIN, (NV == 3 ? 8 : 3)); break;
+    case SPMV_DOT_W: RDC_SPMV_GO(SPMV_DOT_W, (NV == 3 ? 8 : 3)); break;
+    case SPMV_DOT_SELF: RDC_SPMV_GO(SPMV_DOT_SELF, (NV == 3 ? 8 : 3)); break;
+    default: RDC_SPMV_GO(SPMV_RESID, (NV == 3 ? 8 : 3)); break;
+  }
+#undef RDC_SPMV_GO
+}
+
+// the five models' entry masks (models.cuh CMASK|SMASK|TMASK), spelled out here so that solver.cu does not
+// depend on the model code; create_impl checks them against assemble.cu's model_kmask()
+static constexpr unsigned KM_ADPM = 0x15F, KM_RIPF = 0x1F7, KM_HCC = 0x1DF;
+static constexpr unsigned KM_PIHNA = 0x1EFBDEF, KM_PROTEAS = 0x127BDEF;
+
+int spmv_masks_ok() {
+  return model_kmask(RDC_ADPM) == KM_ADPM && model_kmask(RDC_RIPF) == KM_RIPF && model_kmask(RDC_HCC) == KM_HCC &&
+         model_kmask(RDC_PIHNA) == KM_PIHNA && model_kmask(RDC_PROTEAS) == KM_PROTEAS;
+}
+
+static bool spmv_use_tma() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RDC_SPMV_TMA"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+
+template <int NV, unsigned KMASK, int STAGES>
+static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const int4* tiles, const int32_t* rowptr, const int32_t* col,
+                    const double* val, const double* x, double* y, const double* rowscale, const double* w, double* y2,
+                    double* partial, unsigned* counter, double* out, const int* done) {
+  constexpr int SMEM = STAGES * SpmvStage<popc_c(KMASK)>::BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaSuccess;
+#define RDC_TMA_ATTR(MODE) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spmv_tma<NV, KMASK, MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)
+    RDC_TMA_ATTR(SPMV_PLAIN); RDC_TMA_ATTR(SPMV_DOT_W); RDC_TMA_ATTR(SPMV_DOT_SELF); RDC_TMA_ATTR(SPMV_RESID);
+#undef RDC_TMA_ATTR
+    if (e != cudaSuccess) return -1;
+    attr_done = true;
+  }
+#define RDC_TMA_GO(MODE) k_spmv_tma<NV, KMASK, MODE, STAGES><<<grid, RED_THREADS, SMEM, st>>>(n_tiles, tiles, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done)
+  switch (mode) {
+    case SPMV_PLAIN: RDC_TMA_GO(SPMV_PLAIN); break;
+    case SPMV_DOT_W: RDC_TMA_GO(SPMV_DOT_W); break;
+    case SPMV_DOT_SELF: RDC_TMA_GO(SPMV_DOT_SELF); break;
+    default: RDC_TMA_GO(SPMV_RESID); break;
+  }
+#undef RDC_TMA_GO
+  return 0;
+}
+
+// y = S (A x) [+ fused dots, see k_spmv].  `timed` brackets the launch with an event pair (summed lazily).
+static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* rowscale, const double* w, double* y2, double* out,
+                bool check_done, bool timed) {
+  const int n = c->S.n_owned;
+  SolverWork* W = c->work;
+  const int* done = (check_done && W) ? W->state : nullptr;
+  const unsigned grid = (unsigned)spmv_grid(n, c->nv);
+  timed = timed && W && W->n_ev_used < SolverWork::MAX_EV;
+  if (timed) cudaEventRecord(W->ev[2 * W->n_ev_used], c->stream);
+  double* partial = W ? W->partial : nullptr;
+  unsigned* counter = W ? W->counter : nullptr;
+  if (W && W->n_tiles > 0 && spmv_use_tma()) {
+    static int per_sm_env = -1, stages_env = -1;
+    if (per_sm_env < 0) { const char* e = getenv("RDC_TMA_CTAS_PER_SM"); per_sm_env = e ? atoi(e) : 0; }
+    if (stages_env < 0) { const char* e = getenv("RDC_TMA_STAGES"); stages_env = e ? atoi(e) : 0; }
+    const int per_sm = per_sm_env > 0 ? per_sm_env : (c->nv == 3 ? 6 : 2);  // measured: 2 stages x 6 CTAs/SM beats 3 x 4 by 16 %
+    unsigned tg = (unsigned)(W->n_tiles < 148 * per_sm ? W->n_tiles : 148 * per_sm);
+#define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done)
+    int trc;
+    switch (c->model) {
+      case RDC_ADPM: trc = stages_env == 3 ? RDC_TMA_MODEL(3, KM_ADPM, 3) : RDC_TMA_MODEL(3, KM_ADPM, 2); break;
+      case RDC_RIPF: trc = RDC_TMA_MODEL(3, KM_RIPF, 2); break;
+      case RDC_HCC: trc = RDC_TMA_MODEL(3, KM_HCC, 2); break;
+      case RDC_PIHNA: trc = RDC_TMA_MODEL(5, KM_PIHNA, 2); break;
+      default: trc = RDC_TMA_MODEL(5, KM_PROTEAS, 2); break;
+    }
+#undef RDC_TMA_MODEL
+    if (trc) { c->err = "cudaFuncSetAttribute(k_spmv_tma) failed"; return RDC_E_CUDA; }
+  } else {
+#define RDC_SPMV_MODEL(NVV, KM) spmv_mode<NVV, KM>(mode, grid, c->stream, n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done)
+    switch (c->model) {
+      case RDC_ADPM: RDC_SPMV_MODEL(3, KM_ADPM); break;
+      case RDC_RIPF: RDC_SPMV_MODEL(3, KM_RIPF); break;
+      case RDC_HCC: RDC_SPMV_MODEL(3, KM_HCC); break;
+      case RDC_PIHNA: RDC_SPMV_MODEL(5, KM_PIHNA); break;
+      default: RDC_SPMV_MODEL(5, KM_PROTEAS); break;
+    }
+#undef RDC_SPMV_MODEL
+  }
+  if (timed) { cudaEventRecord(W->ev[2 * W->n_ev_used + 1], c->stream); W->n_ev_used++; }
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done) {
+  return spmv(c, SPMV_PLAIN, x, y, rowscale, nullptr, nullptr, nullptr, check_done, check_done);
 }
 
 // out[k] = <V_k, w> for k < nvec (nvec <= 8*NCH) and, when with_norm, out[nvec] = <w, w>.  One pass over w and
@@ -480,7 +817,7 @@ int solver_init(rdc_ctx* c) {
   const size_t vb = W->vec_len * sizeof(double);
   RDC_CUDA(cudaMalloc(&W->t0, vb)); RDC_CUDA(cudaMalloc(&W->t1, vb));
   RDC_CUDA(cudaMemsetAsync(W->t0, 0, vb, c->stream)); RDC_CUDA(cudaMemsetAsync(W->t1, 0, vb, c->stream));
-  RDC_CUDA(cudaMalloc(&W->partial, sizeof(double) * RED_BLOCKS * 33));
+  RDC_CUDA(cudaMalloc(&W->partial, sizeof(double) * (RED_BLOCKS * 33 > 2 * SPMV_MAX_GRID ? RED_BLOCKS * 33 : 2 * SPMV_MAX_GRID)));
   RDC_CUDA(cudaMalloc(&W->counter, sizeof(unsigned)));
   RDC_CUDA(cudaMemsetAsync(W->counter, 0, sizeof(unsigned), c->stream));
   RDC_CUDA(cudaMalloc(&W->scal, sizeof(double) * 32));
@@ -491,6 +828,28 @@ int solver_init(rdc_ctx* c) {
   RDC_CUDA(cudaMallocHost(&W->h_state, sizeof(int) * 8));
   RDC_CUDA(cudaMalloc(&W->h, sizeof(double) * 1024));
   for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) RDC_CUDA(cudaEventCreate(&W->ev[k]));
+  {  // SpMV tiles: consecutive rows, at most SPMV_TILE_ROWS rows and SPMV_CAPB blocks each
+    const std::vector<int32_t>& rp = c->S.rowptr;
+    const int32_t no = c->S.n_owned;
+    std::vector<int4> tl;
+    tl.reserve((size_t)no / SPMV_TILE_ROWS + 16);
+    bool ok = true;
+    for (int32_t r = 0; r < no;) {
+      int32_t e = r;
+      while (e < no && e - r < SPMV_TILE_ROWS && rp[e + 1] - rp[r] <= SPMV_CAPB) e++;
+      if (e == r) { ok = false; break; }   // a single row longer than a stage: keep the LDG kernel
+      tl.push_back(make_int4(r, e - r, rp[r], rp[e] - rp[r]));
+      r = e;
+    }
+    if (ok && !tl.empty()) {
+      RDC_CUDA(cudaMalloc(&W->tiles, tl.size() * sizeof(int4)));
+      RDC_CUDA(cudaMemcpyAsync(W->tiles, tl.data(), tl.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+      RDC_CUDA(cudaStreamSynchronize(c->stream));
+      W->n_tiles = (int)tl.size();
+    }
+  }
+  for (int k = 0; k < SolverWork::RING; k++) RDC_CUDA(cudaEventCreateWithFlags(&W->ev_ring[k], cudaEventDisableTiming));
+  RDC_CUDA(cudaMallocHost(&W->h_ring, sizeof(int) * SolverWork::RING));
   return 0;
 }
 
@@ -528,6 +887,9 @@ void solver_free(rdc_ctx* c) {
   cudaFree(W->g); cudaFree(W->y); cudaFree(W->scal); cudaFree(W->state);
   cudaFreeHost(W->h_scal); cudaFreeHost(W->h_state);
   for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) cudaEventDestroy(W->ev[k]);
+  for (int k = 0; k < SolverWork::RING; k++) cudaEventDestroy(W->ev_ring[k]);
+  cudaFreeHost(W->h_ring);
+  cudaFree(W->tiles);
   delete W;
   c->work = nullptr;
 }
@@ -745,31 +1107,67 @@ static int pcg(rdc_ctx* c, const double* scale, double rtol, int maxits, int* it
   return 0;
 }
 
-// ---- BiCGStab on the left-preconditioned system B A x = B b: fused vector kernels, scalars on the device ----
-// p = r + beta (p - omega v)
-__global__ void k_bi_p(size_t n, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p,
-                       const double* __restrict__ S, const int* __restrict__ done) {
-  if (*done) return;
-  const double beta = S[S_BETA], omega = S[S_OMEGA];
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+// ---- BiCGStab on the left-preconditioned system B A x = B b ---------------------------------------------
+// Five launches per iteration: p-update, SpMV (+<r0,v>), s-update, SpMV (+<s,t>,<t,t>), x/r-update (+<r0,r>,<r,r>).
+// No scalar kernels: the dot products land in the slot table D[] below (all-reduced in place when distributed) and
+// every consumer derives alpha / omega / beta / the convergence decision from D in its prologue -- all threads
+// compute the same values, block 0 records them.  The p-update of iteration `it` is also the convergence check of
+// iteration it-1; the host reads the flag through a pipelined asynchronous copy, a few iterations late, while the
+// kernels already queued return at once.
+enum { D_R0V = 1, D_TS = 2, D_TT = 3, D_XR0 = 4 /* {<r0,r>,<r,r>} parity 0; parity 1 at 6,7 */, D_INIT = 8 /* {<r,r>, ||Bb||^2} */ };
+enum { S_BNORM = 5 };  // next to S_RES / S_TARGET above
+
+__device__ __forceinline__ double bi_target(const double* D, double rtol) { return fmax(rtol * sqrt(D[D_INIT + 1]), 1e-50); }
+
+// p = r + beta (p - omega v)    (it == 0: p = r).  rn / ro: slots of the newest and the previous <r0,r>.
+__global__ void __launch_bounds__(RED_THREADS) k_bi_p(size_t n, int it, int rn, int ro, double rtol, const double* __restrict__ r,
+                                                      const double* __restrict__ v, double* __restrict__ p,
+                                                      const double* __restrict__ D, double* __restrict__ S, int* state) {
+  if (state[0]) return;
+  const double rho = D[rn], rr = D[rn + (it == 0 ? 0 : 1)];
+  const double res = sqrt(rr), target = bi_target(D, rtol);
+  double beta = 0.0, omega = 0.0;
+  int stop = 0, bad = 0;
+  if (!(res == res)) { stop = 1; bad = 1; }
+  else if (res <= target) stop = 1;
+  else if (it > 0) {
+    const double rho_old = D[ro];
+    const double alpha = rho_old / D[D_R0V];
+    omega = D[D_TT] != 0.0 ? D[D_TS] / D[D_TT] : 0.0;
+    if (omega == 0.0 || rho == 0.0) { stop = 1; bad = 1; }
+    beta = (rho / rho_old) * (alpha / omega);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    S[S_RES] = res; S[S_TARGET] = target; S[S_BNORM] = sqrt(D[D_INIT + 1]);
+    state[1] = it;
+    if (stop) { state[3] = bad; __threadfence(); state[0] = 1; }
+  }
+  if (stop) return;
+  if (it == 0) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = r[i];
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+  }
 }
 // s = r - alpha v
-__global__ void k_bi_s(size_t n, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ s,
-                       const double* __restrict__ S, const int* __restrict__ done) {
-  if (*done) return;
-  const double alpha = S[S_ALPHA];
+__global__ void __launch_bounds__(RED_THREADS) k_bi_s(size_t n, int ro, const double* __restrict__ r, const double* __restrict__ v,
+                                                      double* __restrict__ s, const double* __restrict__ D,
+                                                      const int* __restrict__ state) {
+  if (state[0]) return;
+  const double alpha = D[ro] / D[D_R0V];
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     s[i] = fma(-alpha, v[i], r[i]);
 }
 // x += alpha p + omega s ; r = s - omega t ; out = {<r0,r>, <r,r>}
-__global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, double* __restrict__ x, const double* __restrict__ p,
+__global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, int ro, double* __restrict__ x, const double* __restrict__ p,
                                                        const double* __restrict__ s, const double* __restrict__ t,
                                                        double* __restrict__ r, const double* __restrict__ r0,
-                                                       const double* __restrict__ S, double* partial, unsigned* counter,
-                                                       double* out, const int* __restrict__ done) {
-  if (*done) return;
-  const double alpha = S[S_ALPHA], omega = S[S_OMEGA];
+                                                       const double* __restrict__ D, double* partial, unsigned* counter,
+                                                       double* out, const int* __restrict__ state) {
+  if (state[0]) return;
+  const double alpha = D[ro] / D[D_R0V];
+  const double omega = D[D_TT] != 0.0 ? D[D_TS] / D[D_TT] : 0.0;
   double acc[2] = {0.0, 0.0};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double si = s[i];
@@ -781,31 +1179,6 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, double* __restr
   }
   grid_reduce<2>(acc, 2, partial, counter, out);
 }
-__global__ void k_bi_alpha(const double* d, double* S, int* state) {  // alpha = rho / <r0, v>
-  if (state[0]) return;
-  S[S_ALPHA] = S[S_RHO] / d[0];
-}
-__global__ void k_bi_omega(const double* d, double* S, int* state) {  // omega = <t,s>/<t,t>
-  if (state[0]) return;
-  S[S_OMEGA] = d[1] != 0.0 ? d[0] / d[1] : 0.0;
-}
-// after the x/r update: rho, beta for the next iteration, residual norm, convergence / breakdown
-__global__ void k_bi_next(const double* d, double* S, int* state) {
-  if (state[0]) return;
-  const double rho_old = S[S_RHO], rho = d[0];
-  S[S_RHO_OLD] = rho_old;
-  S[S_RHO] = rho;
-  S[S_BETA] = (rho / rho_old) * (S[S_ALPHA] / S[S_OMEGA]);
-  const double res = sqrt(d[1]);
-  S[S_RES] = res;
-  state[1] += 1;
-  if (!(res == res)) { state[0] = 1; state[3] = 1; }
-  else if (res <= S[S_TARGET]) state[0] = 1;
-  else if (S[S_OMEGA] == 0.0 || rho == 0.0) { state[0] = 1; state[3] = 1; }
-}
-__global__ void k_bi_init(const double* d, double* S) {  // rho = <r0,r0> ; res = ||r0||
-  S[S_RHO] = d[0]; S[S_RHO_OLD] = d[0]; S[S_BETA] = 0.0; S[S_OMEGA] = 0.0; S[S_ALPHA] = 0.0; S[S_RES] = sqrt(d[0]);
-}
 
 static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
   SolverWork* W = c->work;
@@ -814,53 +1187,51 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
   rc = ensure_gmres(c, 2);  // borrow V for two more vectors
   if (rc) return rc;
   const size_t n = (size_t)c->S.n_owned * c->nv;
-  static int sync_every = -1;
-  if (sync_every < 0) { const char* e = getenv("RDC_SYNC_EVERY"); sync_every = e ? atoi(e) : 4; if (sync_every < 1) sync_every = 1; }
+  static int depth_env = -1;  // iterations queued ahead of the convergence flag the host has seen
+  if (depth_env < 0) { const char* e = getenv("RDC_SYNC_EVERY"); depth_env = e ? atoi(e) : 0; }
+  // collectives cannot return early once convergence is flagged, so fewer iterations are queued ahead when distributed
+  int depth = depth_env > 0 ? depth_env : (c->S.nranks > 1 ? 2 : 4);
+  if (depth > SolverWork::RING) depth = SolverWork::RING;
   double *r = W->t1, *r0 = W->t2, *p = W->t3, *v = W->t4, *s = W->V, *t = W->V + W->vec_len;
+  double* D = W->h;
+  const unsigned vg = grid_for(n);
   RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
-  k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, scale, W->t0);
-  if ((rc = multidot(c, 0, W->t0, W->t0, true))) return rc;
-  k_set_target<<<1, 1, 0, c->stream>>>(W->h, rtol, W->scal);
+  // r = r0 = B (b - A x), <r,r>, ||B b||^2 in one pass over the operator
   if ((rc = halo_exchange(c, c->d_u))) return rc;
-  if ((rc = launch_spmv(c, c->d_u, W->t0, nullptr, false))) return rc;
-  k_residual<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, W->t0, scale, r);   // r = B(b - A x)
-  c->st.kernel_launches += 3;
-  RDC_CUDA(cudaMemcpyAsync(r0, r, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  RDC_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), c->stream));
-  RDC_CUDA(cudaMemsetAsync(v, 0, n * sizeof(double), c->stream));
-  if ((rc = multidot(c, 0, r, r, true))) return rc;
-  k_bi_init<<<1, 1, 0, c->stream>>>(W->h, W->scal);
-  c->st.kernel_launches++;
-  if ((rc = poll(c))) return rc;
-  if (W->h_scal[S_RES] <= W->h_scal[S_TARGET]) { *its_out = 0; *res_out = W->h_scal[S_RES]; c->st.resnorm0 = W->h_scal[5]; return 0; }
-  int its = 0;
-  while (its < maxits) {
-    k_bi_p<<<grid_for(n), 256, 0, c->stream>>>(n, r, v, p, W->scal, W->state);
-    if ((rc = halo_exchange(c, p))) return rc;
-    if ((rc = launch_spmv(c, p, v, scale, true))) return rc;                 // v = B A p
-    if ((rc = multidot(c, 1, r0, v, false))) return rc;                      // <r0, v>
-    k_bi_alpha<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
-    k_bi_s<<<grid_for(n), 256, 0, c->stream>>>(n, r, v, s, W->scal, W->state);
-    if ((rc = halo_exchange(c, s))) return rc;
-    if ((rc = launch_spmv(c, s, t, scale, true))) return rc;                 // t = B A s
-    if ((rc = multidot(c, 1, s, t, true))) return rc;                        // <s,t>, <t,t>
-    k_bi_omega<<<1, 1, 0, c->stream>>>(W->h, W->scal, W->state);
-    k_bi_xr<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, c->d_u, p, s, t, r, r0, W->scal, W->partial, W->counter,
-                                                      W->h + 64, W->state);
-    if ((rc = allreduce_sum(c, W->h + 64, 2))) return rc;
-    k_bi_next<<<1, 1, 0, c->stream>>>(W->h + 64, W->scal, W->state);
-    c->st.kernel_launches += 6;
-    RDC_CUDA(cudaGetLastError());
-    its++;
-    if (its % sync_every == 0 || its >= maxits) {
-      if ((rc = poll(c))) return rc;
-      if (W->h_state[0]) break;
+  if ((rc = spmv(c, SPMV_RESID, c->d_u, r, scale, c->d_rhs, r0, D + D_INIT, false, false))) return rc;
+  if ((rc = allreduce_sum(c, D + D_INIT, 2))) return rc;
+  // ring of pipelined polls: the flag written by the p-update of iteration `it` is copied to h_ring[it % depth]
+  // and looked at `depth` iterations later, when the copy has long completed -> no pipeline bubble
+  for (int it = 0;; it++) {
+    const int rn = it == 0 ? D_INIT : D_XR0 + 2 * ((it - 1) & 1);
+    const int ro = it <= 1 ? D_INIT : D_XR0 + 2 * ((it - 2) & 1);
+    k_bi_p<<<vg, RED_THREADS, 0, c->stream>>>(n, it, rn, ro, rtol, r, v, p, D, W->scal, W->state);
+    c->st.kernel_launches++;
+    if (it >= maxits) break;
+    const int slot = it % depth;
+    if (it >= depth) {
+      RDC_CUDA(cudaEventSynchronize(W->ev_ring[slot]));
+      if (W->h_ring[slot]) break;
     }
+    RDC_CUDA(cudaMemcpyAsync(W->h_ring + slot, W->state, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    RDC_CUDA(cudaEventRecord(W->ev_ring[slot], c->stream));
+    if ((rc = halo_exchange(c, p))) return rc;
+    if ((rc = spmv(c, SPMV_DOT_W, p, v, scale, r0, nullptr, D + D_R0V, true, true))) return rc;         // v = B A p, <r0,v>
+    if ((rc = allreduce_sum(c, D + D_R0V, 1))) return rc;
+    k_bi_s<<<vg, RED_THREADS, 0, c->stream>>>(n, rn, r, v, s, D, W->state);
+    if ((rc = halo_exchange(c, s))) return rc;
+    if ((rc = spmv(c, SPMV_DOT_SELF, s, t, scale, nullptr, nullptr, D + D_TS, true, true))) return rc;  // t = B A s, <s,t>, <t,t>
+    if ((rc = allreduce_sum(c, D + D_TS, 2))) return rc;
+    double* xr_out = D + D_XR0 + 2 * (it & 1);
+    k_bi_xr<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, rn, c->d_u, p, s, t, r, r0, D, W->partial, W->counter, xr_out, W->state);
+    if ((rc = allreduce_sum(c, xr_out, 2))) return rc;
+    c->st.kernel_launches += 2;
+    RDC_CUDA(cudaGetLastError());
   }
   if ((rc = poll(c))) return rc;
   *its_out = W->h_state[1];
   *res_out = W->h_scal[S_RES];
-  c->st.resnorm0 = W->h_scal[5];
+  c->st.resnorm0 = W->h_scal[S_BNORM];
   if (W->h_state[3]) { c->err = "BiCGStab breakdown"; return RDC_E_DIVERGED; }
   return 0;
 }
@@ -868,9 +1239,7 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
 int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int restart, int* its, double* res) {
   const double* scale = nullptr;
   if (pc == RDC_PC_JACOBI) {
-    int rc = launch_extract_diag(c);
-    if (rc) return rc;
-    scale = c->d_dinv;
+    scale = c->d_dinv;  // written by the assembly kernel next to the diagonal blocks
   } else if (pc != RDC_PC_NONE) {
     c->err = "preconditioner not implemented on the device path (use RDC_PC_JACOBI or RDC_PC_NONE)";
     return RDC_E_ARG;
@@ -883,8 +1252,17 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   else if (ksp == RDC_KSP_CG) rc = pcg(c, scale, rtol, maxits, its, res);
   else if (ksp == RDC_KSP_BICGSTAB) rc = bicgstab(c, scale, rtol, maxits, its, res);
   else { c->err = "unknown ksp"; return RDC_E_ARG; }
-  // Sum of the event-bracketed SpMV launches of this solve.  Launches issued after convergence return at
-  // once (device-side flag) and add ~0, so the mean over the REAL SpMVs is total / (its * spmv per its).
+  // The event-bracketed SpMV launches of this solve are summed lazily (solver_spmv_time) so that the solve
+  // does not end with a host synchronisation.  Launches issued after convergence return at once (device-side
+  // flag) and add ~0, so the mean over the REAL SpMVs is total / (its * spmv per its).
+  W->spmv_time_pending = true;
+  c->st.n_spmv = (*its) * (ksp == RDC_KSP_BICGSTAB ? 2 : 1);
+  return rc;
+}
+
+void solver_spmv_time(rdc_ctx* c) {
+  SolverWork* W = c->work;
+  if (!W || !W->spmv_time_pending) return;
   cudaStreamSynchronize(c->stream);
   double tot = 0.0;
   for (int k = 0; k < W->n_ev_used; k++) {
@@ -892,8 +1270,7 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
     if (cudaEventElapsedTime(&ms, W->ev[2 * k], W->ev[2 * k + 1]) == cudaSuccess) tot += ms;
   }
   c->st.ms_spmv_total = tot;
-  c->st.n_spmv = (*its) * (ksp == RDC_KSP_BICGSTAB ? 2 : 1);
-  return rc;
+  W->spmv_time_pending = false;
 }
 
 }  // namespace rdc
