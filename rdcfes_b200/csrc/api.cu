@@ -100,6 +100,19 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
   for (int k = 0; k < 2; k++) { cudaEventCreate(&c->ev_asm[k]); cudaEventCreate(&c->ev_sol[k]); cudaEventCreate(&c->ev_clamp[k]); }
   if (upload_fe_tables()) { c->err = "cannot upload the reference-element tables"; return fail(RDC_E_CUDA); }
 
+  if (nranks > 1) {  // communicator and peer-memory arena first: the exchanged vectors live inside the arena
+    if (!uid) { c->err = "rdc_create_distributed needs the NCCL unique id"; return fail(RDC_E_ARG); }
+    if ((rc = comm_init(c, uid, c->err))) return fail(rc);
+    std::string p2p_note;
+    if ((rc = p2p_init(c, p2p_note))) return fail(rc);
+    if (getenv("RDC_VERBOSE")) fprintf(stderr, "[rdc rank %d] peer-memory exchange: %s %s\n", rank, (c->p2p && c->p2p->on) ? "on" : "off", p2p_note.c_str());
+  }
+  auto vec_alloc = [&](double** dst, size_t n) -> int {  // arena slot when available (ghost exchange over NVLink stores)
+    double* p = p2p_alloc(c, n);
+    if (p) { *dst = p; return 0; }
+    RDC_CUDA(cudaMalloc(dst, n * sizeof(double)));
+    return 0;
+  };
   auto go = [&]() -> int {
     int r;
     if ((r = upload(c, &c->d_conn, S.conn))) return r;
@@ -137,7 +150,8 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     }
     if ((r = upload(c, &c->d_dofmap, dm))) return r;
     const size_t vb = (size_t)S.n_loc * nv * sizeof(double);
-    RDC_CUDA(cudaMalloc(&c->d_u, vb)); RDC_CUDA(cudaMalloc(&c->d_uold, vb)); RDC_CUDA(cudaMalloc(&c->d_uolder, vb));
+    if ((r = vec_alloc(&c->d_u, (size_t)S.n_loc * nv))) return r;
+    RDC_CUDA(cudaMalloc(&c->d_uold, vb)); RDC_CUDA(cudaMalloc(&c->d_uolder, vb));
     RDC_CUDA(cudaMemsetAsync(c->d_u, 0, vb, c->stream)); RDC_CUDA(cudaMemsetAsync(c->d_uold, 0, vb, c->stream));
     RDC_CUDA(cudaMemsetAsync(c->d_uolder, 0, vb, c->stream));
     RDC_CUDA(cudaMalloc(&c->d_rhs, (size_t)S.n_owned * nv * sizeof(double)));
@@ -145,7 +159,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     RDC_CUDA(cudaMalloc(&c->d_val, (size_t)c->nnzb * c->nkv * sizeof(double) + 64));
     RDC_CUDA(cudaMalloc(&c->d_stage, (size_t)c->D_glob * sizeof(double)));
     if (model == RDC_RIPF) {
-      RDC_CUDA(cudaMalloc(&c->d_td, (size_t)S.n_loc * 3 * sizeof(double)));
+      if ((r = vec_alloc(&c->d_td, (size_t)S.n_loc * 3))) return r;
       RDC_CUDA(cudaMemsetAsync(c->d_td, 0, (size_t)S.n_loc * 3 * sizeof(double), c->stream));
       RDC_CUDA(cudaMalloc(&c->d_prev, (size_t)S.n_owned * 3 * sizeof(double)));
     }
@@ -158,10 +172,6 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     return 0;
   };
   if ((rc = go())) return fail(rc);
-  if (nranks > 1) {
-    if (!uid) { c->err = "rdc_create_distributed needs the NCCL unique id"; return fail(RDC_E_ARG); }
-    if ((rc = comm_init(c, uid, c->err))) return fail(rc);
-  }
   // algorithmic byte counts, local to this rank
   {
     const int64_t Nl = S.n_loc, El = S.E_loc, nnzb = c->nnzb, No = S.n_owned;
@@ -203,8 +213,10 @@ extern "C" void rdc_destroy(rdc_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  comm_destroy(c);
   solver_free(c);
+  if (p2p_owns(c, c->d_u)) c->d_u = nullptr;
+  if (p2p_owns(c, c->d_td)) c->d_td = nullptr;
+  comm_destroy(c);
   cudaFree(c->d_conn); cudaFree(c->d_xyz); cudaFree(c->d_efield); cudaFree(c->d_n2e_ptr); cudaFree(c->d_pair);
   cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_diag_blk); cudaFree(c->d_cta_node); cudaFree(c->d_cptr);
   cudaFree(c->d_clist); cudaFree(c->d_dofmap); cudaFree(c->d_val); cudaFree(c->d_rhs); cudaFree(c->d_dinv);

@@ -11,6 +11,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "rdc_internal.h"
 
@@ -22,6 +25,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -45,6 +49,7 @@ static NcclApi* load_nccl(std::string& err) {
   SYM(CommInitRank, "ncclCommInitRank");
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(GroupStart, "ncclGroupStart");
@@ -86,15 +91,147 @@ int comm_init(rdc_ctx* c, const void* uid, std::string& err) {
 }
 
 void comm_destroy(rdc_ctx* c) {
+  if (c->p2p) {
+    P2P* P = c->p2p;
+    for (int q = 0; q < (int)P->peer.size(); q++)
+      if (q != c->S.rank && P->peer[q]) cudaIpcCloseMemHandle(P->peer[q]);
+    cudaFree(P->d_peer); cudaFree(P->d_counter); cudaFree(P->d_scratch);
+    if (c->comm && c->nccl && P->arena) {  // nobody unmaps an arena that a peer may still be writing to
+      cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(P->arena);
+    delete P;
+    c->p2p = nullptr;
+  }
   if (c->comm && c->nccl) c->nccl->CommDestroy((ncclComm_t)c->comm);
   c->comm = nullptr;
+}
+
+// ---- peer-memory set-up ------------------------------------------------------------------------------------
+// Collective over the NCCL communicator: agrees on the arena geometry (slot = the largest local vector of any
+// rank), exchanges the cudaIpc handles of the arenas and the table that tells a sender where its segment starts
+// in each receiver's ghost tail.  Any failure leaves the NCCL path in place (P2P.on stays false) -- but the
+// decision is all-reduced so that every rank takes the same path.
+int p2p_init(rdc_ctx* c, std::string& err) {
+  const char* e = getenv("RDC_P2P");
+  const int nr = c->S.nranks, me = c->S.rank;
+  if (nr < 2 || nr > RDC_MAX_RANKS || (e && atoi(e) == 0)) return 0;
+  ncclComm_t comm = (ncclComm_t)c->comm;
+  P2P* P = new P2P();
+  c->p2p = P;
+  const int NSLOT = 8;
+  // table contributed by every rank: {n_owned, vec_len, ghosts received from rank 0..nr-1 (offsets), ok flag}
+  const int TW = nr + 4;
+  std::vector<long long> mine((size_t)TW, 0), all((size_t)TW * nr, 0);
+  mine[0] = c->S.n_owned;
+  mine[1] = (long long)c->S.n_loc * c->nv;
+  {
+    std::vector<long long> off((size_t)nr, -1);
+    for (size_t k = 0; k < c->S.nbr_rank.size(); k++) off[c->S.nbr_rank[k]] = c->S.recv_ptr[k];
+    for (int q = 0; q < nr; q++) mine[2 + q] = off[q];
+  }
+  long long* d_tab = nullptr;
+  auto fail = [&](const std::string& why) {
+    err = why;
+    if (d_tab) cudaFree(d_tab);
+    return 0;  // not fatal: NCCL path stays
+  };
+  if (cudaMalloc(&d_tab, sizeof(long long) * TW * (nr + 1)) != cudaSuccess) return fail("p2p: cudaMalloc failed");
+  cudaMemcpyAsync(d_tab, mine.data(), sizeof(long long) * TW, cudaMemcpyHostToDevice, c->stream);
+  if (c->nccl->AllGather(d_tab, d_tab + TW, (size_t)TW * sizeof(long long), ncclChar, comm, c->stream) != ncclSuccess)
+    return fail("p2p: ncclAllGather failed");
+  cudaMemcpyAsync(all.data(), d_tab + TW, sizeof(long long) * TW * nr, cudaMemcpyDeviceToHost, c->stream);
+  cudaStreamSynchronize(c->stream);
+  long long max_len = 0;
+  for (int q = 0; q < nr; q++) max_len = std::max(max_len, all[(size_t)q * TW + 1]);
+  P->slot_bytes = (((size_t)max_len * sizeof(double)) + 255) / 256 * 256;
+  P->nslots = NSLOT;
+  P->arena_bytes = P->header_bytes + P->slot_bytes * NSLOT;
+  int ok = 1;
+  if (cudaMalloc((void**)&P->arena, P->arena_bytes) != cudaSuccess) { ok = 0; P->arena = nullptr; }
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  if (ok) {
+    cudaMemsetAsync(P->arena, 0, P->arena_bytes, c->stream);
+    if (cudaIpcGetMemHandle(&h, P->arena) != cudaSuccess) ok = 0;
+  }
+  // exchange handles (+ ok flags)
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  const int HW = 64 + 8;
+  std::vector<unsigned char> hmine((size_t)HW, 0), hall((size_t)HW * nr, 0);
+  memcpy(hmine.data(), &h, 64);
+  hmine[64] = (unsigned char)ok;
+  unsigned char* d_h = nullptr;
+  if (cudaMalloc(&d_h, (size_t)HW * (nr + 1)) != cudaSuccess) return fail("p2p: cudaMalloc failed");
+  cudaMemcpyAsync(d_h, hmine.data(), HW, cudaMemcpyHostToDevice, c->stream);
+  bool gathered = c->nccl->AllGather(d_h, d_h + HW, (size_t)HW, ncclChar, comm, c->stream) == ncclSuccess;
+  cudaMemcpyAsync(hall.data(), d_h + HW, (size_t)HW * nr, cudaMemcpyDeviceToHost, c->stream);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(d_h);
+  if (!gathered) return fail("p2p: ncclAllGather failed");
+  for (int q = 0; q < nr; q++) ok &= hall[(size_t)q * HW + 64];
+  P->peer.assign((size_t)nr, nullptr);
+  if (ok) {
+    for (int q = 0; q < nr && ok; q++) {
+      if (q == me) { P->peer[q] = P->arena; continue; }
+      cudaIpcMemHandle_t hq;
+      memcpy(&hq, hall.data() + (size_t)q * HW, 64);
+      if (cudaIpcOpenMemHandle(&P->peer[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        P->peer[q] = nullptr;
+        ok = 0;
+      }
+    }
+  }
+  // every rank must take the same path: min over ranks of the local outcome (re-uses the table buffer)
+  {
+    long long v = ok;
+    cudaMemcpyAsync(d_tab, &v, sizeof(long long), cudaMemcpyHostToDevice, c->stream);
+    // ncclMin on int64
+    bool r = c->nccl->AllReduce(d_tab, d_tab, 1, ncclInt64, ncclMin, comm, c->stream) == ncclSuccess;
+    cudaMemcpyAsync(&v, d_tab, sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    ok = r ? (int)v : 0;
+  }
+  cudaFree(d_tab);
+  d_tab = nullptr;
+  if (!ok) return fail("p2p: cudaIpc mapping of a peer arena failed; NCCL send/recv stays in use");
+  // where my segment starts in each neighbour's ghost tail
+  P->dst_node_off.clear();
+  for (size_t k = 0; k < c->S.nbr_rank.size(); k++) {
+    const int q = c->S.nbr_rank[k];
+    const long long n_owned_q = all[(size_t)q * TW + 0], off = all[(size_t)q * TW + 2 + me];
+    if (off < 0 && c->S.send_ptr[k + 1] > c->S.send_ptr[k]) return fail("p2p: inconsistent neighbour tables");
+    P->dst_node_off.push_back(n_owned_q + (off < 0 ? 0 : off));
+  }
+  if (cudaMalloc((void**)&P->d_peer, sizeof(void*) * nr) != cudaSuccess) return fail("p2p: cudaMalloc failed");
+  cudaMemcpyAsync(P->d_peer, P->peer.data(), sizeof(void*) * nr, cudaMemcpyHostToDevice, c->stream);
+  if (cudaMalloc((void**)&P->d_counter, sizeof(unsigned) * RDC_MAX_RANKS) != cudaSuccess) return fail("p2p: cudaMalloc failed");
+  cudaMemsetAsync(P->d_counter, 0, sizeof(unsigned) * RDC_MAX_RANKS, c->stream);
+  if (cudaMalloc((void**)&P->d_scratch, sizeof(double) * 8) != cudaSuccess) return fail("p2p: cudaMalloc failed");
+  cudaMemsetAsync(P->d_scratch, 0, sizeof(double) * 8, c->stream);
+  cudaStreamSynchronize(c->stream);
+  P->on = true;
+  return 0;
+}
+
+double* p2p_alloc(rdc_ctx* c, size_t n_doubles) {
+  P2P* P = c->p2p;
+  if (!P || !P->on || P->slots_used >= P->nslots || n_doubles * sizeof(double) > P->slot_bytes) return nullptr;
+  return (double*)(P->arena + P->header_bytes + (size_t)(P->slots_used++) * P->slot_bytes);
+}
+
+bool p2p_owns(const rdc_ctx* c, const void* p) {
+  const P2P* P = c->p2p;
+  return P && P->on && (const unsigned char*)p >= P->arena && (const unsigned char*)p < P->arena + P->arena_bytes;
 }
 
 int launch_pack(rdc_ctx* c, const double* x, int ncomp);  // solver.cu
 
 // fills the ghost part of x (nv values per node) from the owning ranks
-int halo_exchange(rdc_ctx* c, double* x) {
+int halo_exchange(rdc_ctx* c, double* x, bool check_done) {
   if (c->S.nranks == 1) return 0;
+  if (p2p_owns(c, x)) return p2p_launch_halo(c, x, check_done);
   const int nv = c->nv;
   int rc = launch_pack(c, x, nv);
   if (rc) return rc;
@@ -111,8 +248,10 @@ int halo_exchange(rdc_ctx* c, double* x) {
   return 0;
 }
 
-int allreduce_sum(rdc_ctx* c, double* d_buf, int n) {
+int allreduce_sum(rdc_ctx* c, double* d_buf, int n, bool check_done) {
   if (c->S.nranks == 1 || n == 0) return 0;
+  if (c->p2p && c->p2p->on && n <= 8) return p2p_launch_allreduce(c, d_buf, n, check_done);
+  if (c->p2p) c->p2p->dirty = false;  // an NCCL all-reduce orders the ranks just as well
   RDC_NCCL(c->nccl->AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
   return 0;
 }

@@ -25,6 +25,31 @@ void fe_table_fill(FeTable* T, int elem_type);
 
 struct NcclApi;  // comm.cpp
 
+// ---- NVLink peer-memory exchange (p2p.cu, comm.cpp) ----
+#define RDC_MAX_RANKS 16
+struct P2PHeader {                       // at offset 0 of every rank's arena; written by the peers
+  unsigned long long halo_flag[RDC_MAX_RANKS];
+  unsigned long long ar_flag[2][RDC_MAX_RANKS];
+  double ar_val[2][RDC_MAX_RANKS][8];
+  // all-reduce fused into the producing kernel: one double = two 8-byte words {32 data bits | 32-bit tag}, so data
+  // and flag arrive in the same (atomic) store and one NVLink crossing is the whole latency
+  unsigned long long ll[2][RDC_MAX_RANKS][8][2];
+  int error;
+};
+struct P2P {
+  bool on = false;
+  unsigned char* arena = nullptr;        // cudaMalloc'ed, exported with cudaIpcGetMemHandle
+  size_t arena_bytes = 0, slot_bytes = 0, header_bytes = 8192;
+  int nslots = 0, slots_used = 0;
+  std::vector<void*> peer;               // [nranks] mapped arena base of every rank (own arena for self)
+  void** d_peer = nullptr;
+  std::vector<int64_t> dst_node_off;     // per neighbour: local node offset of MY segment in ITS ghost tail
+  unsigned* d_counter = nullptr;         // per neighbour block counters
+  double* d_scratch = nullptr;
+  unsigned long long halo_seq = 0, ar_seq = 0;
+  bool dirty = false;                    // an exchange happened since the last all-reduce
+};
+
 // Host-side result of the one-time set-up (partition, numbering, pattern, assembly maps).
 struct HostSetup {
   int nen = 0, nv = 0;
@@ -105,6 +130,8 @@ struct rdc_ctx {
   SolverWork* work = nullptr;
 
   // comm
+  rdc::P2P* p2p = nullptr;
+  int* work_state = nullptr;         // solver's device flags (state[0] = done) for the peer-memory kernels
   rdc::NcclApi* nccl = nullptr;
   void* comm = nullptr;              // ncclComm_t
   int32_t* d_send_idx = nullptr;
@@ -133,13 +160,23 @@ void solver_spmv_time(rdc_ctx* c);   // resolves the lazily summed SpMV event ti
 int spmv_masks_ok();                // solver.cu's entry masks agree with the model definitions
 int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc);     // dst_loc[l] = src[dofmap[l]]
 int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob);    // owned part only
-int halo_exchange(rdc_ctx* c, double* x);                                   // fills the ghost part of x
-int allreduce_sum(rdc_ctx* c, double* d_buf, int n);
+int halo_exchange(rdc_ctx* c, double* x, bool check_done = false);          // fills the ghost part of x
+int allreduce_sum(rdc_ctx* c, double* d_buf, int n, bool check_done = false);
 int allreduce_max(rdc_ctx* c, double* d_buf, int n);
 // comm.cpp
 int comm_unique_id(void* out128, std::string& err);
 int comm_init(rdc_ctx* c, const void* uid, std::string& err);
 void comm_destroy(rdc_ctx* c);
+int p2p_init(rdc_ctx* c, std::string& err);        // after comm_init: arena, IPC handles, peer tables
+double* p2p_alloc(rdc_ctx* c, size_t n_doubles);   // vector slot inside the arena (nullptr: not available)
+bool p2p_owns(const rdc_ctx* c, const void* p);
+// p2p.cu
+int p2p_launch_halo(rdc_ctx* c, double* x, bool check_done);
+int p2p_launch_allreduce(rdc_ctx* c, double* d_buf, int n, bool check_done);
+int p2p_check_error(rdc_ctx* c);
+struct HaloArgs;
+void p2p_fill_halo_args(rdc_ctx* c, const double* x, HaloArgs* A, int* max_blk, int* total_blk);
+int p2p_halo_begin(rdc_ctx* c, unsigned long long* seq);
 }  // namespace rdc
 
 #define RDC_CUDA(call)                                                                   \

@@ -15,7 +15,9 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
+#include "p2p_dev.cuh"
 #include "rdc_internal.h"
 
 namespace rdc {
@@ -37,6 +39,8 @@ struct SolverWork {
   double* t2 = nullptr;
   double* t3 = nullptr;
   double* t4 = nullptr;
+  double* hs = nullptr;      // BiCGStab s (exchanged)
+  double* hp2 = nullptr;     // second p buffer (exchanged)
   double* partial = nullptr; // [RED_BLOCKS * (MD_CHUNK+1)]
   unsigned* counter = nullptr;
   double* h = nullptr;       // [restart_cap + 2] dots of the current column (+ norm^2)
@@ -66,12 +70,38 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Distributed runs finish the reduction inside the same kernel (ArCtx::nranks > 1): the last block stores its sums
+// into a slot on every peer (NVLink peer memory, tag-in-word protocol), waits for the slots of all ranks in its own
+// header and adds them in rank order, so every rank gets the bit-identical result without a separate collective.
+struct ArCtx {
+  P2PHeader* const* peer = nullptr;   // [nranks] headers of all ranks (device array)
+  P2PHeader* mine = nullptr;
+  int me = 0, nranks = 1;
+  unsigned long long seq = 0;
+};
+
+__device__ __forceinline__ void ll_store(unsigned long long* slot, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (b & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (b >> 32) | ((unsigned long long)tag << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const unsigned long long* slot, unsigned tag, double* v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) return false;
+  *v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return true;
+}
+
 // Block-reduce NVAL values into partial[k * gridDim.x + blockIdx.x]; the last block to finish adds the partials
 // of all blocks -- thread t takes blocks t, t+256, ... in order, then a fixed shuffle/shared-memory tree -- and
 // writes out[k].  One launch, no float atomics, bit-reproducible for a fixed grid size.
 template <int NVAL>
-__device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double* partial, unsigned* counter, double* out) {
+__device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double* partial, unsigned* counter, double* out,
+                                            const ArCtx& ar = ArCtx()) {
   __shared__ double s_red[RED_THREADS / 32][NVAL];
+  __shared__ double s_tot[NVAL];
   __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -105,8 +135,34 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double*
         double t = 0.0;
 #pragma unroll
         for (int w = 0; w < RED_THREADS / 32; w++) t += s_red[w][0];
-        out[k] = t;
+        s_tot[k] = t;
       }
+    }
+    __syncthreads();
+    if (ar.nranks > 1) {
+      const int par = (int)(ar.seq & 1ull);
+      const unsigned tag = (unsigned)ar.seq;
+      // thread (q, k): my k-th sum -> my slot on rank q ; then rank q's k-th sum <- its slot in my header
+      const int q = threadIdx.x / NVAL, k = threadIdx.x % NVAL;
+      double got = 0.0;
+      if (q < ar.nranks && k < nval) {
+        ll_store(&ar.peer[q]->ll[par][ar.me][k][0], s_tot[k], tag);
+        const unsigned long long t0 = clock64();
+        while (!ll_load(&ar.mine->ll[par][q][k][0], tag, &got)) {
+          if (clock64() - t0 > 8000000000ll) { ar.mine->error = 1; break; }
+        }
+      }
+      __syncthreads();
+      __shared__ double s_in[RDC_MAX_RANKS][NVAL];
+      if (q < ar.nranks && k < nval) s_in[q][k] = got;
+      __syncthreads();
+      if (threadIdx.x < NVAL && threadIdx.x < nval) {
+        double t = 0.0;
+        for (int r = 0; r < ar.nranks; r++) t += s_in[r][threadIdx.x];
+        out[threadIdx.x] = t;
+      }
+    } else if (threadIdx.x < NVAL && threadIdx.x < nval) {
+      out[threadIdx.x] = s_tot[threadIdx.x];
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
@@ -142,7 +198,7 @@ __global__ void __launch_bounds__(RED_THREADS, MINB)
 k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
        const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ rowscale,
        const double* __restrict__ w, double* __restrict__ y2, double* partial, unsigned* counter, double* out,
-       const int* __restrict__ done) {
+       const int* __restrict__ done, const ArCtx ar) {
   if (done && *done) return;
   constexpr int G = 16;
   constexpr int NKV = popc_c(KMASK);
@@ -230,7 +286,7 @@ k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict
       }
     }
   }
-  if (MODE != SPMV_PLAIN) grid_reduce<2>(d, MODE == SPMV_DOT_W ? 1 : 2, partial, counter, out);
+  if (MODE != SPMV_PLAIN) grid_reduce<2>(d, MODE == SPMV_DOT_W ? 1 : 2, partial, counter, out, ar);
 }
 
 // ---- TMA-staged variant (the default) ------------------------------------------------------------------------
@@ -284,7 +340,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 k_spmv_tma(int n_tiles, const int4* __restrict__ tiles, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
            const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ rowscale, const double* __restrict__ w, double* __restrict__ y2, double* partial,
-           unsigned* counter, double* out, const int* __restrict__ done) {
+           unsigned* counter, double* out, const int* __restrict__ done, const ArCtx ar) {
   if (done && *done) return;
   constexpr int G = 16;
   constexpr int NKV = popc_c(KMASK);
@@ -390,7 +446,7 @@ k_spmv_tma(int n_tiles, const int4* __restrict__ tiles, const int32_t* __restric
     }
     __syncthreads();   // the stage may be refilled from the next iteration on
   }
-  if (MODE != SPMV_PLAIN) grid_reduce<2>(d, MODE == SPMV_DOT_W ? 1 : 2, partial, counter, out);
+  if (MODE != SPMV_PLAIN) grid_reduce<2>(d, MODE == SPMV_DOT_W ? 1 : 2, partial, counter, out, ar);
 }
 
 static int spmv_grid(int n_rows, int nv) {
@@ -405,10 +461,10 @@ static int spmv_grid(int n_rows, int nv) {
 template <int NV, unsigned KMASK>
 static void spmv_mode(int mode, unsigned grid, cudaStream_t st, int n, const int32_t* rowptr, const int32_t* col, const double* val,
                       const double* x, double* y, const double* rowscale, const double* w, double* y2, double* partial,
-                      unsigned* counter, double* out, const int* done) {
+                      unsigned* counter, double* out, const int* done, const ArCtx& ar) {
   static int minb = -1;  // tuning knob (3-variable models): resident CTAs per SM the kernel is compiled for
   if (minb < 0) { const char* e = getenv("RDC_SPMV_MINB"); minb = e ? atoi(e) : 4; }
-#define RDC_SPMV_GO(MODE, MB) k_spmv<NV, KMASK, MODE, MB><<<grid, RED_THREADS, 0, st>>>(n, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done)
+#define RDC_SPMV_GO(MODE, MB) k_spmv<NV, KMASK, MODE, MB><<<grid, RED_THREADS, 0, st>>>(n, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
   if (NV == 3 && minb == 4) {
     switch (mode) {
       case SPMV_PLAIN: RDC_SPMV_GO(SPMV_PLAIN, (NV == 3 ? 4 : 3)); break;
@@ -464,7 +520,7 @@ static bool spmv_use_tma() {
 template <int NV, unsigned KMASK, int STAGES>
 static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const int4* tiles, const int32_t* rowptr, const int32_t* col,
                     const double* val, const double* x, double* y, const double* rowscale, const double* w, double* y2,
-                    double* partial, unsigned* counter, double* out, const int* done) {
+                    double* partial, unsigned* counter, double* out, const int* done, const ArCtx& ar) {
   constexpr int SMEM = STAGES * SpmvStage<popc_c(KMASK)>::BYTES;
   static bool attr_done = false;
   if (!attr_done) {
@@ -475,7 +531,7 @@ static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const
     if (e != cudaSuccess) return -1;
     attr_done = true;
   }
-#define RDC_TMA_GO(MODE) k_spmv_tma<NV, KMASK, MODE, STAGES><<<grid, RED_THREADS, SMEM, st>>>(n_tiles, tiles, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done)
+#define RDC_TMA_GO(MODE) k_spmv_tma<NV, KMASK, MODE, STAGES><<<grid, RED_THREADS, SMEM, st>>>(n_tiles, tiles, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
   switch (mode) {
     case SPMV_PLAIN: RDC_TMA_GO(SPMV_PLAIN); break;
     case SPMV_DOT_W: RDC_TMA_GO(SPMV_DOT_W); break;
@@ -487,8 +543,28 @@ static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const
 }
 
 // y = S (A x) [+ fused dots, see k_spmv].  `timed` brackets the launch with an event pair (summed lazily).
+// Context for a reduction that is finished across the ranks by the producing kernel itself (peer-memory path).
+// *fused tells the caller whether the separate all-reduce is still needed (NCCL path / single rank).
+static ArCtx ar_begin(rdc_ctx* c, bool* fused) {
+  ArCtx a;
+  *fused = false;
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("RDC_P2P_FUSED_AR"); en = e ? atoi(e) : 1; }
+  P2P* P = c->p2p;
+  if (!en || !P || !P->on) return a;
+  a.peer = (P2PHeader* const*)P->d_peer;
+  a.mine = (P2PHeader*)P->arena;
+  a.me = c->S.rank;
+  a.nranks = c->S.nranks;
+  a.seq = ++P->ar_seq;
+  P->dirty = false;
+  *fused = true;
+  return a;
+}
+
+// `ar` (optional): finish the fused dot products across the ranks inside the kernel (see ar_begin)
 static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* rowscale, const double* w, double* y2, double* out,
-                bool check_done, bool timed) {
+                bool check_done, bool timed, const ArCtx& ar = ArCtx()) {
   const int n = c->S.n_owned;
   SolverWork* W = c->work;
   const int* done = (check_done && W) ? W->state : nullptr;
@@ -503,7 +579,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
     if (stages_env < 0) { const char* e = getenv("RDC_TMA_STAGES"); stages_env = e ? atoi(e) : 0; }
     const int per_sm = per_sm_env > 0 ? per_sm_env : (c->nv == 3 ? 6 : 2);  // measured: 2 stages x 6 CTAs/SM beats 3 x 4 by 16 %
     unsigned tg = (unsigned)(W->n_tiles < 148 * per_sm ? W->n_tiles : 148 * per_sm);
-#define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done)
+#define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
     int trc;
     switch (c->model) {
       case RDC_ADPM: trc = stages_env == 3 ? RDC_TMA_MODEL(3, KM_ADPM, 3) : RDC_TMA_MODEL(3, KM_ADPM, 2); break;
@@ -515,7 +591,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
 #undef RDC_TMA_MODEL
     if (trc) { c->err = "cudaFuncSetAttribute(k_spmv_tma) failed"; return RDC_E_CUDA; }
   } else {
-#define RDC_SPMV_MODEL(NVV, KM) spmv_mode<NVV, KM>(mode, grid, c->stream, n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done)
+#define RDC_SPMV_MODEL(NVV, KM) spmv_mode<NVV, KM>(mode, grid, c->stream, n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
     switch (c->model) {
       case RDC_ADPM: RDC_SPMV_MODEL(3, KM_ADPM); break;
       case RDC_RIPF: RDC_SPMV_MODEL(3, KM_RIPF); break;
@@ -823,6 +899,7 @@ int solver_init(rdc_ctx* c) {
   RDC_CUDA(cudaMalloc(&W->scal, sizeof(double) * 32));
   RDC_CUDA(cudaMemsetAsync(W->scal, 0, sizeof(double) * 32, c->stream));
   RDC_CUDA(cudaMalloc(&W->state, sizeof(int) * 8));
+  c->work_state = W->state;
   RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
   RDC_CUDA(cudaMallocHost(&W->h_scal, sizeof(double) * 32));
   RDC_CUDA(cudaMallocHost(&W->h_state, sizeof(int) * 8));
@@ -849,7 +926,8 @@ int solver_init(rdc_ctx* c) {
     }
   }
   for (int k = 0; k < SolverWork::RING; k++) RDC_CUDA(cudaEventCreateWithFlags(&W->ev_ring[k], cudaEventDisableTiming));
-  RDC_CUDA(cudaMallocHost(&W->h_ring, sizeof(int) * SolverWork::RING));
+  RDC_CUDA(cudaHostAlloc(&W->h_ring, sizeof(int) * SolverWork::RING, cudaHostAllocMapped));
+  memset(W->h_ring, 0, sizeof(int) * SolverWork::RING);
   return 0;
 }
 
@@ -873,7 +951,13 @@ static int ensure_extra_vectors(rdc_ctx* c) {
   SolverWork* W = c->work;
   if (W->t2) return 0;
   const size_t vb = W->vec_len * sizeof(double);
-  RDC_CUDA(cudaMalloc(&W->t2, vb)); RDC_CUDA(cudaMalloc(&W->t3, vb)); RDC_CUDA(cudaMalloc(&W->t4, vb));
+  RDC_CUDA(cudaMalloc(&W->t2, vb)); RDC_CUDA(cudaMalloc(&W->t4, vb));
+  // the two vectors whose ghosts are exchanged every iteration (p and s) live in the peer-memory arena when there is one
+  if (!(W->t3 = p2p_alloc(c, W->vec_len))) RDC_CUDA(cudaMalloc(&W->t3, vb));
+  if (!(W->hs = p2p_alloc(c, W->vec_len))) RDC_CUDA(cudaMalloc(&W->hs, vb));
+  if (!(W->hp2 = p2p_alloc(c, W->vec_len))) RDC_CUDA(cudaMalloc(&W->hp2, vb));
+  RDC_CUDA(cudaMemsetAsync(W->hp2, 0, vb, c->stream));
+  RDC_CUDA(cudaMemsetAsync(W->hs, 0, vb, c->stream));
   RDC_CUDA(cudaMemsetAsync(W->t2, 0, vb, c->stream)); RDC_CUDA(cudaMemsetAsync(W->t3, 0, vb, c->stream));
   RDC_CUDA(cudaMemsetAsync(W->t4, 0, vb, c->stream));
   return 0;
@@ -882,7 +966,10 @@ static int ensure_extra_vectors(rdc_ctx* c) {
 void solver_free(rdc_ctx* c) {
   SolverWork* W = c->work;
   if (!W) return;
-  cudaFree(W->V); cudaFree(W->t0); cudaFree(W->t1); cudaFree(W->t2); cudaFree(W->t3); cudaFree(W->t4);
+  cudaFree(W->V); cudaFree(W->t0); cudaFree(W->t1); cudaFree(W->t2); cudaFree(W->t4);
+  if (!p2p_owns(c, W->t3)) cudaFree(W->t3);
+  if (!p2p_owns(c, W->hs)) cudaFree(W->hs);
+  if (!p2p_owns(c, W->hp2)) cudaFree(W->hp2);
   cudaFree(W->partial); cudaFree(W->counter); cudaFree(W->h); cudaFree(W->H); cudaFree(W->cs); cudaFree(W->sn);
   cudaFree(W->g); cudaFree(W->y); cudaFree(W->scal); cudaFree(W->state);
   cudaFreeHost(W->h_scal); cudaFreeHost(W->h_state);
@@ -1119,11 +1206,29 @@ enum { S_BNORM = 5 };  // next to S_RES / S_TARGET above
 
 __device__ __forceinline__ double bi_target(const double* D, double rtol) { return fmax(rtol * sqrt(D[D_INIT + 1]), 1e-50); }
 
-// p = r + beta (p - omega v)    (it == 0: p = r).  rn / ro: slots of the newest and the previous <r0,r>.
+// Bundle of the ghost exchange that a vector kernel performs for the vector it produces (distributed runs): the
+// first hb.total blocks of the grid recompute the boundary entries (same expression, same inputs -> same bits as the
+// main blocks) and store them straight into the neighbours' ghost tails; see p2p.cu.
+struct HaloBundle {
+  HaloArgs A;
+  const int32_t* send_idx = nullptr;
+  unsigned* counter = nullptr;
+  P2PHeader* hdr = nullptr;
+  unsigned long long seq = 0;
+  int total = 0;   // number of exchange blocks at the front of the grid (0: no exchange)
+  int nv = 1;
+};
+
+// p_new = r + beta (p_old - omega v)    (it == 0: p_new = r).  rn / ro: slots of the newest and the previous <r0,r>.
 __global__ void __launch_bounds__(RED_THREADS) k_bi_p(size_t n, int it, int rn, int ro, double rtol, const double* __restrict__ r,
-                                                      const double* __restrict__ v, double* __restrict__ p,
-                                                      const double* __restrict__ D, double* __restrict__ S, int* state) {
-  if (state[0]) return;
+                                                      const double* __restrict__ v, const double* __restrict__ p_old,
+                                                      double* __restrict__ p_new, const double* __restrict__ D,
+                                                      double* __restrict__ S, int* state, volatile int* host_flag,
+                                                      const HaloBundle hb) {
+  if (state[0]) {  // converged earlier: tell the host (zero-copy pinned memory), nothing else to do
+    if (blockIdx.x == 0 && threadIdx.x == 0) *host_flag = (it + 1) | (1 << 30);
+    return;
+  }
   const double rho = D[rn], rr = D[rn + (it == 0 ? 0 : 1)];
   const double res = sqrt(rr), target = bi_target(D, rtol);
   double beta = 0.0, omega = 0.0;
@@ -1137,34 +1242,63 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_p(size_t n, int it, int rn, 
     if (omega == 0.0 || rho == 0.0) { stop = 1; bad = 1; }
     beta = (rho / rho_old) * (alpha / omega);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == (unsigned)hb.total && threadIdx.x == 0) {   // first main block keeps the books
     S[S_RES] = res; S[S_TARGET] = target; S[S_BNORM] = sqrt(D[D_INIT + 1]);
     state[1] = it;
     if (stop) { state[3] = bad; __threadfence(); state[0] = 1; }
+    *host_flag = (it + 1) | (stop << 30);
   }
-  if (stop) return;
+  if (stop) return;   // every rank takes the same decision from the same all-reduced values: nobody exchanges
+  if ((int)blockIdx.x < hb.total) {
+    int k = 0;
+    while ((int)blockIdx.x >= hb.A.blk_ptr[k + 1]) k++;
+    const int nb = hb.A.nblk[k], b = (int)blockIdx.x - hb.A.blk_ptr[k];
+    const int s0 = hb.A.send_ptr[k], cnt = (hb.A.send_ptr[k + 1] - s0) * hb.nv;
+    double* dst = hb.A.dst[k];
+    for (int i = b * blockDim.x + threadIdx.x; i < cnt; i += nb * blockDim.x) {
+      const int node = i / hb.nv, a = i - node * hb.nv;
+      const size_t j = (size_t)hb.send_idx[s0 + node] * hb.nv + a;
+      dst[i] = it == 0 ? r[j] : fma(beta, fma(-omega, v[j], p_old[j]), r[j]);
+    }
+    halo_publish_and_wait(hb.A, k, nb, hb.counter, hb.hdr, hb.seq);
+    return;
+  }
+  const size_t first = (blockIdx.x - hb.total) * (size_t)blockDim.x + threadIdx.x, step = (size_t)(gridDim.x - hb.total) * blockDim.x;
   if (it == 0) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = r[i];
+    for (size_t i = first; i < n; i += step) p_new[i] = r[i];
   } else {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-      p[i] = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+    for (size_t i = first; i < n; i += step) p_new[i] = fma(beta, fma(-omega, v[i], p_old[i]), r[i]);
   }
 }
-// s = r - alpha v
+// s = r - alpha v   (+ ghost exchange of s, see HaloBundle)
 __global__ void __launch_bounds__(RED_THREADS) k_bi_s(size_t n, int ro, const double* __restrict__ r, const double* __restrict__ v,
                                                       double* __restrict__ s, const double* __restrict__ D,
-                                                      const int* __restrict__ state) {
+                                                      const int* __restrict__ state, const HaloBundle hb) {
   if (state[0]) return;
   const double alpha = D[ro] / D[D_R0V];
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    s[i] = fma(-alpha, v[i], r[i]);
+  if ((int)blockIdx.x < hb.total) {
+    int k = 0;
+    while ((int)blockIdx.x >= hb.A.blk_ptr[k + 1]) k++;
+    const int nb = hb.A.nblk[k], b = (int)blockIdx.x - hb.A.blk_ptr[k];
+    const int s0 = hb.A.send_ptr[k], cnt = (hb.A.send_ptr[k + 1] - s0) * hb.nv;
+    double* dst = hb.A.dst[k];
+    for (int i = b * blockDim.x + threadIdx.x; i < cnt; i += nb * blockDim.x) {
+      const int node = i / hb.nv, a = i - node * hb.nv;
+      const size_t j = (size_t)hb.send_idx[s0 + node] * hb.nv + a;
+      dst[i] = fma(-alpha, v[j], r[j]);
+    }
+    halo_publish_and_wait(hb.A, k, nb, hb.counter, hb.hdr, hb.seq);
+    return;
+  }
+  const size_t first = (blockIdx.x - hb.total) * (size_t)blockDim.x + threadIdx.x, step = (size_t)(gridDim.x - hb.total) * blockDim.x;
+  for (size_t i = first; i < n; i += step) s[i] = fma(-alpha, v[i], r[i]);
 }
 // x += alpha p + omega s ; r = s - omega t ; out = {<r0,r>, <r,r>}
 __global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, int ro, double* __restrict__ x, const double* __restrict__ p,
                                                        const double* __restrict__ s, const double* __restrict__ t,
                                                        double* __restrict__ r, const double* __restrict__ r0,
                                                        const double* __restrict__ D, double* partial, unsigned* counter,
-                                                       double* out, const int* __restrict__ state) {
+                                                       double* out, const int* __restrict__ state, const ArCtx ar) {
   if (state[0]) return;
   const double alpha = D[ro] / D[D_R0V];
   const double omega = D[D_TT] != 0.0 ? D[D_TS] / D[D_TT] : 0.0;
@@ -1177,58 +1311,140 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, int ro, double*
     acc[0] = fma(r0[i], ri, acc[0]);
     acc[1] = fma(ri, ri, acc[1]);
   }
-  grid_reduce<2>(acc, 2, partial, counter, out);
+  grid_reduce<2>(acc, 2, partial, counter, out, ar);
 }
+
+static bool fused_halo_ok(rdc_ctx* c, const double* x) {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("RDC_P2P_FUSED_HALO"); en = e ? atoi(e) : 1; }
+  return en && c->S.nranks > 1 && p2p_owns(c, x) && !c->S.nbr_rank.empty();
+}
+// describe the exchange of arena vector x for a fused vector kernel (bookkeeping as in p2p_launch_halo)
+static int halo_bundle(rdc_ctx* c, const double* x, HaloBundle* hb) {
+  int max_blk = 1;
+  p2p_fill_halo_args(c, x, &hb->A, &max_blk, &hb->total);
+  hb->send_idx = c->d_send_idx;
+  hb->counter = c->p2p->d_counter;
+  hb->hdr = (P2PHeader*)c->p2p->arena;
+  hb->nv = c->nv;
+  return p2p_halo_begin(c, &hb->seq);
+}
+
+// RDC_TRACE=1: event-bracket every operation of BiCGStab iteration 4 and print the device time of each (debug aid)
+struct IterTrace {
+  static constexpr int N = 24;
+  cudaEvent_t ev[N];
+  const char* name[N];
+  int n = 0;
+  bool on = false, made = false;
+  void mark(const char* what, cudaStream_t st) {
+    if (!on || n >= N) return;
+    if (!made) { for (int k = 0; k < N; k++) cudaEventCreate(&ev[k]); made = true; }
+    name[n] = what;
+    cudaEventRecord(ev[n++], st);
+  }
+  void report(int rank) {
+    if (!on || n < 2) return;
+    cudaEventSynchronize(ev[n - 1]);
+    char line[1024];
+    int o = snprintf(line, sizeof(line), "[rdc trace rank %d]", rank);
+    for (int k = 1; k < n; k++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+      o += snprintf(line + o, sizeof(line) - o, " %s=%.1fus", name[k], ms * 1e3f);
+    }
+    fprintf(stderr, "%s\n", line);
+    n = 0;
+  }
+};
 
 static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
   SolverWork* W = c->work;
+  static IterTrace TR;
+  static int trace_env = -1;
+  if (trace_env < 0) { const char* e = getenv("RDC_TRACE"); trace_env = e ? atoi(e) : 0; }
   int rc = ensure_extra_vectors(c);
   if (rc) return rc;
-  rc = ensure_gmres(c, 2);  // borrow V for two more vectors
+  rc = ensure_gmres(c, 1);  // borrow V for one more vector
   if (rc) return rc;
   const size_t n = (size_t)c->S.n_owned * c->nv;
   static int depth_env = -1;  // iterations queued ahead of the convergence flag the host has seen
   if (depth_env < 0) { const char* e = getenv("RDC_SYNC_EVERY"); depth_env = e ? atoi(e) : 0; }
   // collectives cannot return early once convergence is flagged, so fewer iterations are queued ahead when distributed
   int depth = depth_env > 0 ? depth_env : (c->S.nranks > 1 ? 2 : 4);
-  if (depth > SolverWork::RING) depth = SolverWork::RING;
-  double *r = W->t1, *r0 = W->t2, *p = W->t3, *v = W->t4, *s = W->V, *t = W->V + W->vec_len;
+  if (depth > SolverWork::RING - 1) depth = SolverWork::RING - 1;
+  double *r = W->t1, *r0 = W->t2, *v = W->t4, *s = W->hs, *t = W->V;
+  double* pbuf[2] = {W->t3, W->hp2};   // p is double-buffered: the exchange blocks of the p-update read the old p
   double* D = W->h;
   const unsigned vg = grid_for(n);
   RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
+  memset(W->h_ring, 0, sizeof(int) * SolverWork::RING);  // the previous solve ended with a stream synchronisation
   // r = r0 = B (b - A x), <r,r>, ||B b||^2 in one pass over the operator
   if ((rc = halo_exchange(c, c->d_u))) return rc;
-  if ((rc = spmv(c, SPMV_RESID, c->d_u, r, scale, c->d_rhs, r0, D + D_INIT, false, false))) return rc;
-  if ((rc = allreduce_sum(c, D + D_INIT, 2))) return rc;
-  // ring of pipelined polls: the flag written by the p-update of iteration `it` is copied to h_ring[it % depth]
-  // and looked at `depth` iterations later, when the copy has long completed -> no pipeline bubble
+  bool fused;
+  {
+    const ArCtx ar = ar_begin(c, &fused);
+    if ((rc = spmv(c, SPMV_RESID, c->d_u, r, scale, c->d_rhs, r0, D + D_INIT, false, false, ar))) return rc;
+    if (!fused && (rc = allreduce_sum(c, D + D_INIT, 2))) return rc;
+  }
+  // pipelined polls without stream work: the p-update of iteration `it` stores its decision in a ring of pinned,
+  // device-mapped host words; the host looks at the word of iteration it-depth, which has long been written
   for (int it = 0;; it++) {
     const int rn = it == 0 ? D_INIT : D_XR0 + 2 * ((it - 1) & 1);
     const int ro = it <= 1 ? D_INIT : D_XR0 + 2 * ((it - 2) & 1);
-    k_bi_p<<<vg, RED_THREADS, 0, c->stream>>>(n, it, rn, ro, rtol, r, v, p, D, W->scal, W->state);
+    TR.on = trace_env && it == 4;
+    TR.mark("start", c->stream);
+    const int slot = it % SolverWork::RING;
+    double *p = pbuf[it & 1], *p_old = pbuf[(it + 1) & 1];
+    HaloBundle hb;
+    const bool fuse_halo = fused_halo_ok(c, p) && fused_halo_ok(c, s);
+    if (fuse_halo && it < maxits) { if ((rc = halo_bundle(c, p, &hb))) return rc; }
+    k_bi_p<<<vg + hb.total, RED_THREADS, 0, c->stream>>>(n, it, rn, ro, rtol, r, v, p_old, p, D, W->scal, W->state, W->h_ring + slot, hb);
+    TR.mark("p_update", c->stream);
     c->st.kernel_launches++;
     if (it >= maxits) break;
-    const int slot = it % depth;
-    if (it >= depth) {
-      RDC_CUDA(cudaEventSynchronize(W->ev_ring[slot]));
-      if (W->h_ring[slot]) break;
+    if (it >= depth) {  // the p-update of iteration it-depth wrote (it-depth+1) | stop<<30 straight into pinned host memory
+      volatile int* f = W->h_ring + (it - depth) % SolverWork::RING;
+      int spins = 0;
+      while ((*f & 0x3fffffff) != it - depth + 1) {
+        if (++spins > 2000) {  // it should be there already; fall back to waiting for the stream (also surfaces errors)
+          RDC_CUDA(cudaStreamSynchronize(c->stream));
+          if ((*f & 0x3fffffff) != it - depth + 1) { c->err = "BiCGStab: convergence flag never arrived"; return RDC_E_CUDA; }
+        }
+      }
+      if (*f >> 30) break;
     }
-    RDC_CUDA(cudaMemcpyAsync(W->h_ring + slot, W->state, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    RDC_CUDA(cudaEventRecord(W->ev_ring[slot], c->stream));
-    if ((rc = halo_exchange(c, p))) return rc;
-    if ((rc = spmv(c, SPMV_DOT_W, p, v, scale, r0, nullptr, D + D_R0V, true, true))) return rc;         // v = B A p, <r0,v>
-    if ((rc = allreduce_sum(c, D + D_R0V, 1))) return rc;
-    k_bi_s<<<vg, RED_THREADS, 0, c->stream>>>(n, rn, r, v, s, D, W->state);
-    if ((rc = halo_exchange(c, s))) return rc;
-    if ((rc = spmv(c, SPMV_DOT_SELF, s, t, scale, nullptr, nullptr, D + D_TS, true, true))) return rc;  // t = B A s, <s,t>, <t,t>
-    if ((rc = allreduce_sum(c, D + D_TS, 2))) return rc;
+    TR.mark("poll", c->stream);
+    if (!fuse_halo && (rc = halo_exchange(c, p, true))) return rc;
+    TR.mark("halo_p", c->stream);
+    ArCtx ar = ar_begin(c, &fused);
+    if ((rc = spmv(c, SPMV_DOT_W, p, v, scale, r0, nullptr, D + D_R0V, true, true, ar))) return rc;     // v = B A p, <r0,v>
+    TR.mark("spmv1", c->stream);
+    if (!fused && (rc = allreduce_sum(c, D + D_R0V, 1, true))) return rc;
+    TR.mark("ar1", c->stream);
+    hb = HaloBundle();
+    if (fuse_halo && (rc = halo_bundle(c, s, &hb))) return rc;
+    k_bi_s<<<vg + hb.total, RED_THREADS, 0, c->stream>>>(n, rn, r, v, s, D, W->state, hb);
+    TR.mark("s_update", c->stream);
+    if (!fuse_halo && (rc = halo_exchange(c, s, true))) return rc;
+    TR.mark("halo_s", c->stream);
+    ar = ar_begin(c, &fused);
+    if ((rc = spmv(c, SPMV_DOT_SELF, s, t, scale, nullptr, nullptr, D + D_TS, true, true, ar))) return rc;  // t = B A s, <s,t>, <t,t>
+    TR.mark("spmv2", c->stream);
+    if (!fused && (rc = allreduce_sum(c, D + D_TS, 2, true))) return rc;
+    TR.mark("ar2", c->stream);
     double* xr_out = D + D_XR0 + 2 * (it & 1);
-    k_bi_xr<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, rn, c->d_u, p, s, t, r, r0, D, W->partial, W->counter, xr_out, W->state);
-    if ((rc = allreduce_sum(c, xr_out, 2))) return rc;
+    ar = ar_begin(c, &fused);
+    k_bi_xr<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, rn, c->d_u, p, s, t, r, r0, D, W->partial, W->counter, xr_out, W->state, ar);
+    TR.mark("xr_update", c->stream);
+    if (!fused && (rc = allreduce_sum(c, xr_out, 2, true))) return rc;
+    TR.mark("ar3", c->stream);
+    TR.report(c->S.rank);
     c->st.kernel_launches += 2;
     RDC_CUDA(cudaGetLastError());
   }
   if ((rc = poll(c))) return rc;
+  if ((rc = p2p_check_error(c))) return rc;
   *its_out = W->h_state[1];
   *res_out = W->h_scal[S_RES];
   c->st.resnorm0 = W->h_scal[S_BNORM];
