@@ -182,6 +182,9 @@ int rdc_update_coords(rdc_ctx*, const double* xyz /* [n_nodes*3] */);
 /* u is indexed by global dof id (length rdc_n_dofs).  Sets solution == current_local_solution. */
 int rdc_set_solution(rdc_ctx*, const double* u);
 int rdc_get_solution(rdc_ctx*, double* u);      /* distributed: every rank receives the full vector */
+/* distributed: writes only the entries of the dofs owned by this rank (no all-gather); single rank: == rdc_get_solution.
+ * Replaces the rank-local part of system.solution that libMesh keeps per processor (PETSc MPI vector). */
+int rdc_get_solution_owned(rdc_ctx*, double* u);
 int rdc_get_old_solution(rdc_ctx*, double* u);
 int64_t rdc_n_dofs(const rdc_ctx*);
 int rdc_set_time(rdc_ctx*, double time);        /* system.time (adpm.C:64) */
@@ -233,6 +236,10 @@ int rdc_probe_partition(int elem_type, int nvars, int64_t n_nodes, int64_t n_ele
                         const double* xyz, int rank, int nranks, int partitioner, int32_t* n_owned, int32_t* n_ghost,
                         int64_t* n_elems_local, int32_t** owner, int32_t* n_nbr, int32_t** nbr_rank,
                         int32_t** send_ptr, int32_t** send_glob, int32_t** recv_ptr, int32_t** recv_glob);
+/* Tuning switch of the context (defaults: environment RDC_<NAME>): "spmv_tma" 1/0 (TMA-staged or LDG SpMV),
+ * "spmv_minb", "spmv_ctas_per_sm", "tma_ctas_per_sm", "tma_stages", "sync_every", "p2p_fused_ar",
+ * "p2p_fused_halo", "trace".  Results do not depend on them beyond floating-point summation order. */
+int rdc_set_option(rdc_ctx*, const char* name, int value);
 /* run every kernel on this cudaStream_t (default: a stream owned by the context) */
 int rdc_set_stream(rdc_ctx*, void* cuda_stream);
 const char* rdc_version(void);

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <ctype.h>
 
 #include <algorithm>
 #include <new>
@@ -16,6 +17,30 @@ int pairs_per_cta_for(int model, int etype);  // assemble.cu
 using namespace rdc;
 
 static std::string g_create_err;
+
+struct OptName { const char* name; int rdc_options::*field; };
+static const OptName kOptions[] = {
+    {"spmv_tma", &rdc_options::spmv_tma}, {"spmv_minb", &rdc_options::spmv_minb},
+    {"spmv_ctas_per_sm", &rdc_options::spmv_ctas_per_sm}, {"tma_ctas_per_sm", &rdc_options::tma_ctas_per_sm},
+    {"tma_stages", &rdc_options::tma_stages}, {"sync_every", &rdc_options::sync_every},
+    {"p2p_fused_ar", &rdc_options::p2p_fused_ar}, {"p2p_fused_halo", &rdc_options::p2p_fused_halo},
+    {"trace", &rdc_options::trace}};
+
+static void options_from_env(rdc_options& o) {
+  for (const OptName& k : kOptions) {
+    std::string env = "RDC_";
+    for (const char* p = k.name; *p; p++) env += (char)toupper(*p);
+    if (const char* e = getenv(env.c_str())) o.*(k.field) = atoi(e);
+  }
+}
+
+extern "C" int rdc_set_option(rdc_ctx* c, const char* name, int value) {
+  if (!c || !name) return RDC_E_ARG;
+  for (const OptName& k : kOptions)
+    if (!strcmp(k.name, name)) { c->opt.*(k.field) = value; return RDC_OK; }
+  c->err = std::string("rdc_set_option: unknown option ") + name;
+  return RDC_E_ARG;
+}
 
 extern "C" const char* rdc_version(void) { return "rdcfes_b200 0.1 (sm_100a)"; }
 
@@ -73,6 +98,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
   c->model = model; c->etype = elem_type; c->nen = elem_type == RDC_TET4 ? 4 : 8; c->nv = nv;
   c->nqp = elem_type == RDC_TET4 ? 5 : 8;
   c->device = device;
+  options_from_env(c->opt);
   c->kmask = model_kmask(model);
   c->nkv = __builtin_popcount(c->kmask);
   if (!spmv_masks_ok()) { g_create_err = "internal: SpMV entry masks differ from the model definitions"; delete c; return RDC_E_STATE; }
@@ -316,11 +342,25 @@ extern "C" int rdc_update_coords(rdc_ctx* c, const double* xyz) {
   return RDC_OK;
 }
 
+// true when `p` is pinned / registered host memory that kernels can address directly (zero-copy over PCIe)
+static bool host_is_mapped(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost && a.devicePointer != nullptr;
+}
+
 // host vector in global dof order -> local device vector (owned + ghosts)
 static int to_device(rdc_ctx* c, const double* host, double* d_loc) {
   if (c->identity_dofs) {
     RDC_CUDA(cudaMemcpyAsync(d_loc, host, (size_t)c->D_glob * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     return 0;
+  }
+  if (host_is_mapped(host)) {
+    // a rank needs only its own n_loc*v entries: gather them straight out of the pinned host buffer instead of
+    // staging the whole global vector (distributed runs move 1/nranks of the bytes)
+    cudaPointerAttributes a;
+    cudaPointerGetAttributes(&a, host);
+    return launch_gather(c, (const double*)a.devicePointer, d_loc);
   }
   RDC_CUDA(cudaMemcpyAsync(c->d_stage, host, (size_t)c->D_glob * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   return launch_gather(c, c->d_stage, d_loc);
@@ -358,6 +398,32 @@ extern "C" int rdc_get_solution(rdc_ctx* c, double* u) {
   CHECK_CTX(c);
   if (!u) return RDC_E_ARG;
   return to_host(c, c->d_u, u);
+}
+
+// Only the entries of the dofs OWNED by this rank are written (global dof indexing, the rest of u is left alone):
+// what a distributed caller needs to refresh its own part of a PETSc-style vector without the all-gather.
+extern "C" int rdc_get_solution_owned(rdc_ctx* c, double* u) {
+  CHECK_CTX(c);
+  if (!u) return RDC_E_ARG;
+  if (c->S.nranks == 1) return to_host(c, c->d_u, u);
+  if (host_is_mapped(u)) {
+    cudaPointerAttributes a;
+    cudaPointerGetAttributes(&a, u);
+    int rc = launch_scatter(c, c->d_u, (double*)a.devicePointer);   // zero-copy stores into the pinned buffer
+    if (rc) return rc;
+    RDC_CUDA(cudaStreamSynchronize(c->stream));
+    return RDC_OK;
+  }
+  const size_t n = (size_t)c->S.n_owned * c->nv;
+  std::vector<double> tmp(n);
+  RDC_CUDA(cudaMemcpyAsync(tmp.data(), c->d_u, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  RDC_CUDA(cudaStreamSynchronize(c->stream));
+  for (int32_t l = 0; l < c->S.n_owned; l++) {
+    const int32_t g = c->S.loc2glob[l];
+    const int32_t base = c->dof_base.empty() ? g * c->nv : c->dof_base[g];
+    for (int a2 = 0; a2 < c->nv; a2++) u[base + a2] = tmp[(size_t)l * c->nv + a2];
+  }
+  return RDC_OK;
 }
 
 extern "C" int rdc_get_old_solution(rdc_ctx* c, double* u) {

@@ -85,6 +85,20 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
 
 struct SolverWork;  // solver.cu
 
+// Tuning switches of one context.  Defaults come from the environment (RDC_<NAME> upper case) at rdc_create and
+// can be changed with rdc_set_option; the parity tests use them to run the alternative kernels side by side.
+struct rdc_options {
+  int spmv_tma = 1;            // 1: TMA bulk-copy staged SpMV ; 0: LDG SpMV
+  int spmv_minb = 4;           // LDG SpMV: resident CTAs per SM the kernel is compiled for (4, 5, 6, 8)
+  int spmv_ctas_per_sm = 0;    // LDG SpMV grid (0 = default)
+  int tma_ctas_per_sm = 0;     // TMA SpMV grid (0 = default)
+  int tma_stages = 0;          // TMA SpMV stages (0 = default 2 ; 3)
+  int sync_every = 0;          // iterations queued ahead of the convergence flag (0 = default)
+  int p2p_fused_ar = 1;        // all-reduce finished inside the producing kernel
+  int p2p_fused_halo = 1;      // ghost exchange inside the BiCGStab vector kernels
+  int trace = 0;               // print the device time of every operation of BiCGStab iteration 4
+};
+
 struct rdc_ctx {
   int model = 0, etype = 0, nen = 0, nv = 0, nqp = 0;
   int device = 0;
@@ -137,6 +151,7 @@ struct rdc_ctx {
   int32_t* d_send_idx = nullptr;
   double* d_sendbuf = nullptr;
 
+  rdc_options opt;
   // stats
   rdc_stats st = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;          // scratch pair (rdc_bench_spmv)

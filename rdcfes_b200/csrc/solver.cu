@@ -449,9 +449,7 @@ k_spmv_tma(int n_tiles, const int4* __restrict__ tiles, const int32_t* __restric
   if (MODE != SPMV_PLAIN) grid_reduce<2>(d, MODE == SPMV_DOT_W ? 1 : 2, partial, counter, out, ar);
 }
 
-static int spmv_grid(int n_rows, int nv) {
-  static int per_sm = -1;
-  if (per_sm < 0) { const char* e = getenv("RDC_SPMV_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; }
+static int spmv_grid(int n_rows, int nv, int per_sm) {
   const int want = (n_rows + 15) / 16;
   int cap = 148 * (per_sm > 0 ? per_sm : (nv == 3 ? 4 : 3));
   if (cap > SPMV_MAX_GRID) cap = SPMV_MAX_GRID;   // bounded number of per-CTA partials for the fused dots
@@ -459,11 +457,9 @@ static int spmv_grid(int n_rows, int nv) {
 }
 
 template <int NV, unsigned KMASK>
-static void spmv_mode(int mode, unsigned grid, cudaStream_t st, int n, const int32_t* rowptr, const int32_t* col, const double* val,
+static void spmv_mode(int minb, int mode, unsigned grid, cudaStream_t st, int n, const int32_t* rowptr, const int32_t* col, const double* val,
                       const double* x, double* y, const double* rowscale, const double* w, double* y2, double* partial,
                       unsigned* counter, double* out, const int* done, const ArCtx& ar) {
-  static int minb = -1;  // tuning knob (3-variable models): resident CTAs per SM the kernel is compiled for
-  if (minb < 0) { const char* e = getenv("RDC_SPMV_MINB"); minb = e ? atoi(e) : 4; }
 #define RDC_SPMV_GO(MODE, MB) k_spmv<NV, KMASK, MODE, MB><<<grid, RED_THREADS, 0, st>>>(n, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
   if (NV == 3 && minb == 4) {
     switch (mode) {
@@ -511,12 +507,6 @@ int spmv_masks_ok() {
          model_kmask(RDC_PIHNA) == KM_PIHNA && model_kmask(RDC_PROTEAS) == KM_PROTEAS;
 }
 
-static bool spmv_use_tma() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("RDC_SPMV_TMA"); v = e ? atoi(e) : 1; }
-  return v != 0;
-}
-
 template <int NV, unsigned KMASK, int STAGES>
 static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const int4* tiles, const int32_t* rowptr, const int32_t* col,
                     const double* val, const double* x, double* y, const double* rowscale, const double* w, double* y2,
@@ -548,10 +538,8 @@ static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const
 static ArCtx ar_begin(rdc_ctx* c, bool* fused) {
   ArCtx a;
   *fused = false;
-  static int en = -1;
-  if (en < 0) { const char* e = getenv("RDC_P2P_FUSED_AR"); en = e ? atoi(e) : 1; }
   P2P* P = c->p2p;
-  if (!en || !P || !P->on) return a;
+  if (!c->opt.p2p_fused_ar || !P || !P->on) return a;
   a.peer = (P2PHeader* const*)P->d_peer;
   a.mine = (P2PHeader*)P->arena;
   a.me = c->S.rank;
@@ -568,15 +556,13 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
   const int n = c->S.n_owned;
   SolverWork* W = c->work;
   const int* done = (check_done && W) ? W->state : nullptr;
-  const unsigned grid = (unsigned)spmv_grid(n, c->nv);
+  const unsigned grid = (unsigned)spmv_grid(n, c->nv, c->opt.spmv_ctas_per_sm);
   timed = timed && W && W->n_ev_used < SolverWork::MAX_EV;
   if (timed) cudaEventRecord(W->ev[2 * W->n_ev_used], c->stream);
   double* partial = W ? W->partial : nullptr;
   unsigned* counter = W ? W->counter : nullptr;
-  if (W && W->n_tiles > 0 && spmv_use_tma()) {
-    static int per_sm_env = -1, stages_env = -1;
-    if (per_sm_env < 0) { const char* e = getenv("RDC_TMA_CTAS_PER_SM"); per_sm_env = e ? atoi(e) : 0; }
-    if (stages_env < 0) { const char* e = getenv("RDC_TMA_STAGES"); stages_env = e ? atoi(e) : 0; }
+  if (W && W->n_tiles > 0 && c->opt.spmv_tma) {
+    const int per_sm_env = c->opt.tma_ctas_per_sm, stages_env = c->opt.tma_stages;
     const int per_sm = per_sm_env > 0 ? per_sm_env : (c->nv == 3 ? 6 : 2);  // measured: 2 stages x 6 CTAs/SM beats 3 x 4 by 16 %
     unsigned tg = (unsigned)(W->n_tiles < 148 * per_sm ? W->n_tiles : 148 * per_sm);
 #define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
@@ -591,7 +577,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
 #undef RDC_TMA_MODEL
     if (trc) { c->err = "cudaFuncSetAttribute(k_spmv_tma) failed"; return RDC_E_CUDA; }
   } else {
-#define RDC_SPMV_MODEL(NVV, KM) spmv_mode<NVV, KM>(mode, grid, c->stream, n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
+#define RDC_SPMV_MODEL(NVV, KM) spmv_mode<NVV, KM>(c->opt.spmv_minb, mode, grid, c->stream, n, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
     switch (c->model) {
       case RDC_ADPM: RDC_SPMV_MODEL(3, KM_ADPM); break;
       case RDC_RIPF: RDC_SPMV_MODEL(3, KM_RIPF); break;
@@ -1037,8 +1023,7 @@ static int gmres(rdc_ctx* c, const double* scale, double rtol, int maxits, int m
   if (rc) return rc;
   const size_t n = (size_t)c->S.n_owned * c->nv;
   const size_t ld = W->vec_len;
-  static int sync_every = -1;
-  if (sync_every < 0) { const char* e = getenv("RDC_SYNC_EVERY"); sync_every = e ? atoi(e) : 4; if (sync_every < 1) sync_every = 1; }
+  const int sync_every = c->opt.sync_every > 0 ? c->opt.sync_every : 4;
   RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
   // reference norm ||B b||
   k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, scale, W->t0);
@@ -1143,8 +1128,7 @@ static int pcg(rdc_ctx* c, const double* scale, double rtol, int maxits, int* it
   int rc = ensure_extra_vectors(c);
   if (rc) return rc;
   const size_t n = (size_t)c->S.n_owned * c->nv;
-  static int sync_every = -1;
-  if (sync_every < 0) { const char* e = getenv("RDC_SYNC_EVERY"); sync_every = e ? atoi(e) : 4; if (sync_every < 1) sync_every = 1; }
+  const int sync_every = c->opt.sync_every > 0 ? c->opt.sync_every : 4;
   double *r = W->t1, *z = W->t2, *p = W->t3, *Ap = W->t4;
   RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
   k_mul<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_rhs, scale, W->t0);
@@ -1315,9 +1299,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, int ro, double*
 }
 
 static bool fused_halo_ok(rdc_ctx* c, const double* x) {
-  static int en = -1;
-  if (en < 0) { const char* e = getenv("RDC_P2P_FUSED_HALO"); en = e ? atoi(e) : 1; }
-  return en && c->S.nranks > 1 && p2p_owns(c, x) && !c->S.nbr_rank.empty();
+  return c->opt.p2p_fused_halo && c->S.nranks > 1 && p2p_owns(c, x) && !c->S.nbr_rank.empty();
 }
 // describe the exchange of arena vector x for a fused vector kernel (bookkeeping as in p2p_launch_halo)
 static int halo_bundle(rdc_ctx* c, const double* x, HaloBundle* hb) {
@@ -1361,15 +1343,13 @@ struct IterTrace {
 static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
   SolverWork* W = c->work;
   static IterTrace TR;
-  static int trace_env = -1;
-  if (trace_env < 0) { const char* e = getenv("RDC_TRACE"); trace_env = e ? atoi(e) : 0; }
+  const int trace_env = c->opt.trace;
   int rc = ensure_extra_vectors(c);
   if (rc) return rc;
   rc = ensure_gmres(c, 1);  // borrow V for one more vector
   if (rc) return rc;
   const size_t n = (size_t)c->S.n_owned * c->nv;
-  static int depth_env = -1;  // iterations queued ahead of the convergence flag the host has seen
-  if (depth_env < 0) { const char* e = getenv("RDC_SYNC_EVERY"); depth_env = e ? atoi(e) : 0; }
+  const int depth_env = c->opt.sync_every;  // iterations queued ahead of the convergence flag the host has seen
   // collectives cannot return early once convergence is flagged, so fewer iterations are queued ahead when distributed
   int depth = depth_env > 0 ? depth_env : (c->S.nranks > 1 ? 2 : 4);
   if (depth > SolverWork::RING - 1) depth = SolverWork::RING - 1;

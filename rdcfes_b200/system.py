@@ -112,6 +112,11 @@ class TransientRdcSystem:
         self._check(self._L.rdc_get_solution(self._h, _ptr(out)))
         return out
 
+    def get_solution_owned(self, out):
+        """Refresh only the entries owned by this rank in the global-dof-indexed array `out` (no all-gather)."""
+        self._check(self._L.rdc_get_solution_owned(self._h, _ptr(out)))
+        return out
+
     def get_old_solution(self):
         out = np.empty(self.n_dofs)
         self._check(self._L.rdc_get_old_solution(self._h, _ptr(out)))
@@ -189,6 +194,9 @@ class TransientRdcSystem:
         s = _lib.Stats()
         self._check(self._L.rdc_get_stats(self._h, C.byref(s)))
         return s
+
+    def set_option(self, name: str, value: int):
+        self._check(self._L.rdc_set_option(self._h, name.encode(), int(value)))
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._L.rdc_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
