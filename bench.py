@@ -133,7 +133,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", type=int, default=119, help="cells per edge (119 -> 10.1 M tets)")
-    ap.add_argument("--cpu-n", type=int, default=40, help="sample mesh of the CPU baseline")
+    ap.add_argument("--cpu-n", type=int, default=90, help="sample mesh of the CPU baseline (90 -> 4.4 M tets)")
     ap.add_argument("--ksp", type=int, default=2, help="0 GMRES(30) (libMesh default), 1 CG, 2 BiCGStab; all Jacobi, rtol 1e-12")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partitioner", type=int, default=0)
@@ -252,11 +252,15 @@ def main():
                 "per": "rank" if world > 1 else "job", "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "k_spmv<3> (block-CSR SpMV, fused Jacobi scaling)", "bound": "hbm",
-                     "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak, "traffic": None,
+        "roofline": {"kernel": "k_spmv_tma<3,KMASK_ADPM,*,2> (row-local block-CSR SpMV, TMA-staged, fused Jacobi scaling "
+                               "and BiCGStab dot products)", "bound": "hbm",
+                     "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
+                     # workload on one GPU (profiles/r1d_spmv_tma_full.csv); other sizes were not captured
+                     "traffic": 1.673e9 if (args.n == 119 and world == 1) else None,
                      "peak_source": peak_src, "bytes_per_launch": int(st.bytes_spmv), "ms_per_launch": spmv_ms,
                      "launches_timed": acc["n_spmv"], "frac_of_nominal_8TBs": spmv_gbs / 8000.0},
-        "roofline_assembly": {"kernel": "k_assemble<Adpm,4,256>", "bound": "hbm", "achieved": asm_gbs, "peak": peak,
+        "roofline_assembly": {"kernel": "k_assemble<Adpm,4,128,4> (fp64-pipe bound, see DESIGN.md 4.1)", "bound": "hbm", "achieved": asm_gbs, "peak": peak,
                               "unit": "GB/s", "frac": asm_gbs / peak, "bytes_per_launch": int(st.bytes_assemble),
                               "index_bytes_per_launch": int(st.bytes_index), "ms_per_launch": asm_ms},
         "phases_ms_per_step": {"assemble": asm_ms, "solve": acc["ms_solve"] / args.steps,

@@ -204,6 +204,9 @@ int rdc_spmv(rdc_ctx*, const double* x, double* y);
 /* device-resident repetition of the SpMV kernel for the roofline measurement: returns mean ms */
 int rdc_bench_spmv(rdc_ctx*, int reps, double* mean_ms);
 
+/* read-only streaming probe over the stored operator values (reference point for the SpMV roofline): mean ms, bytes */
+int rdc_bench_stream(rdc_ctx*, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes);
+
 /* ---- parity / introspection ------------------------------------------------------------------- */
 /* Scalar CSR in global dof numbering, rows and columns sorted: exactly the (node graph + I) (x) dense
  * v x v pattern libMesh preallocates.  Buffers are malloc'ed by the library; free

@@ -536,6 +536,21 @@ extern "C" int rdc_bench_spmv(rdc_ctx* c, int reps, double* mean_ms) {
   return rc;
 }
 
+extern "C" int rdc_bench_stream(rdc_ctx* c, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes) {
+  CHECK_CTX(c);
+  if (!c->assembled || reps < 1 || !mean_ms || ctas_per_sm < 1 || ctas_per_sm > 16) return RDC_E_STATE;
+  int rc = launch_stream_probe(c, ctas_per_sm);  // warm-up
+  cudaEventRecord(c->ev0, c->stream);
+  for (int r = 0; r < reps && !rc; r++) rc = launch_stream_probe(c, ctas_per_sm);
+  cudaEventRecord(c->ev1, c->stream);
+  cudaEventSynchronize(c->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  *mean_ms = ms / reps;
+  if (bytes) *bytes = (int64_t)((size_t)c->nnzb * c->nkv / 2 * 16);
+  return rc;
+}
+
 extern "C" int rdc_get_stats(rdc_ctx* c, struct rdc_stats* s) {
   if (!c || !s) return RDC_E_ARG;
   cudaSetDevice(c->device);

@@ -299,6 +299,9 @@ k_spmv(int n_rows, const int32_t* __restrict__ rowptr, const int32_t* __restrict
 // (~15 KB per CTA and stage), the half-warps compute from shared memory and only gather x through L1/L2.
 // What bounds it now is the number of rows whose x gathers are in flight per SM (threads), not the stream:
 // 2 stages x 6 CTAs/SM (96 rows) measured 0.334 ms, 3 stages x 4 CTAs/SM (64 rows) 0.397 ms on the headline case.
+// Tried and measured without gain: tile descriptors pipelined STAGES deep in registers (0.332 ms), x gathers issued
+// one tile ahead with 3 stages x 4 CTAs/SM (0.355 ms).  A read-only stream over the same array reaches 6.7 TB/s
+// (rdc_bench_stream), the plain SpMV 5.2-5.5 TB/s, the SpMV inside BiCGStab (fused dots, cold x) 4.9 TB/s.
 // Tiles are cut on the host (<= 16 rows, <= SPMV_CAPB blocks): {row0, nrows, first block, nblocks}.
 static constexpr int SPMV_CAPB = 256;
 static constexpr int SPMV_TILE_ROWS = 16;
@@ -1454,6 +1457,28 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   W->spmv_time_pending = true;
   c->st.n_spmv = (*its) * (ksp == RDC_KSP_BICGSTAB ? 2 : 1);
   return rc;
+}
+
+// Read-only streaming probe over the operator values (16-byte loads, fixed-order reduction): the bandwidth a pure
+// read of the same array reaches on this GPU, as a reference point next to the SpMV roofline.
+__global__ void __launch_bounds__(RED_THREADS) k_stream_read(size_t n2, const double2* __restrict__ a, double* partial,
+                                                             unsigned* counter, double* out) {
+  double acc[1] = {0.0};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(a + i));
+    acc[0] += v.x + v.y;
+  }
+  grid_reduce<1>(acc, 1, partial, counter, out);
+}
+
+int launch_stream_probe(rdc_ctx* c, int ctas_per_sm) {
+  SolverWork* W = c->work;
+  const size_t n2 = (size_t)c->nnzb * c->nkv / 2;
+  k_stream_read<<<148 * ctas_per_sm, RED_THREADS, 0, c->stream>>>(n2, (const double2*)c->d_val, W->partial, W->counter, W->h + 900);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
+  return 0;
 }
 
 void solver_spmv_time(rdc_ctx* c) {

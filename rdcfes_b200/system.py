@@ -174,6 +174,12 @@ class TransientRdcSystem:
         self._check(self._L.rdc_bench_spmv(self._h, reps, C.byref(ms)))
         return ms.value
 
+    def bench_stream(self, reps=20, ctas_per_sm=8):
+        """(mean ms, bytes) of a read-only pass over the stored operator values."""
+        ms, nb = C.c_double(), C.c_int64()
+        self._check(self._L.rdc_bench_stream(self._h, reps, ctas_per_sm, C.byref(ms), C.byref(nb)))
+        return ms.value, nb.value
+
     def download_csr(self):
         """(rows, rowptr, col, val, rhs): scalar CSR of the rows owned by this rank, global dof numbering."""
         n_rows, nnz = C.c_int64(), C.c_int64()
