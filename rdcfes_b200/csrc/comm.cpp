@@ -95,7 +95,7 @@ void comm_destroy(rdc_ctx* c) {
     P2P* P = c->p2p;
     for (int q = 0; q < (int)P->peer.size(); q++)
       if (q != c->S.rank && P->peer[q]) cudaIpcCloseMemHandle(P->peer[q]);
-    cudaFree(P->d_peer); cudaFree(P->d_counter); cudaFree(P->d_scratch);
+    cudaFree(P->d_peer); cudaFree(P->d_scratch);
     if (c->comm && c->nccl && P->arena) {  // nobody unmaps an arena that a peer may still be writing to
       cudaStreamSynchronize(c->stream);
     }
@@ -105,6 +105,11 @@ void comm_destroy(rdc_ctx* c) {
   }
   if (c->comm && c->nccl) c->nccl->CommDestroy((ncclComm_t)c->comm);
   c->comm = nullptr;
+}
+
+static double* p2p_alloc_raw(P2P* P) {
+  if (P->slots_used >= P->nslots) return nullptr;
+  return (double*)(P->arena + P->header_bytes + (size_t)(P->slots_used++) * P->slot_bytes);
 }
 
 // ---- peer-memory set-up ------------------------------------------------------------------------------------
@@ -148,6 +153,7 @@ int p2p_init(rdc_ctx* c, std::string& err) {
   P->nslots = NSLOT;
   P->arena_bytes = P->header_bytes + P->slot_bytes * NSLOT;
   int ok = 1;
+  if ((size_t)c->S.n_ghost * c->nv * 16 > P->slot_bytes) ok = 0;   // staging area of the tagged ghost exchange
   if (cudaMalloc((void**)&P->arena, P->arena_bytes) != cudaSuccess) { ok = 0; P->arena = nullptr; }
   cudaIpcMemHandle_t h;
   memset(&h, 0, sizeof(h));
@@ -202,12 +208,17 @@ int p2p_init(rdc_ctx* c, std::string& err) {
     const int q = c->S.nbr_rank[k];
     const long long n_owned_q = all[(size_t)q * TW + 0], off = all[(size_t)q * TW + 2 + me];
     if (off < 0 && c->S.send_ptr[k + 1] > c->S.send_ptr[k]) return fail("p2p: inconsistent neighbour tables");
-    P->dst_node_off.push_back(n_owned_q + (off < 0 ? 0 : off));
+    (void)n_owned_q;
+    P->dst_node_off.push_back(off < 0 ? 0 : off);
+  }
+  // two staging areas for the tagged ghost exchange (16 B per ghost value), one per parity
+  for (int par = 0; par < 2; par++) {
+    double* sp = p2p_alloc_raw(P);
+    if (!sp) return fail("p2p: arena too small for the ghost staging areas");
+    P->stage_off[par] = (size_t)((unsigned char*)sp - P->arena);
   }
   if (cudaMalloc((void**)&P->d_peer, sizeof(void*) * nr) != cudaSuccess) return fail("p2p: cudaMalloc failed");
   cudaMemcpyAsync(P->d_peer, P->peer.data(), sizeof(void*) * nr, cudaMemcpyHostToDevice, c->stream);
-  if (cudaMalloc((void**)&P->d_counter, sizeof(unsigned) * RDC_MAX_RANKS) != cudaSuccess) return fail("p2p: cudaMalloc failed");
-  cudaMemsetAsync(P->d_counter, 0, sizeof(unsigned) * RDC_MAX_RANKS, c->stream);
   if (cudaMalloc((void**)&P->d_scratch, sizeof(double) * 8) != cudaSuccess) return fail("p2p: cudaMalloc failed");
   cudaMemsetAsync(P->d_scratch, 0, sizeof(double) * 8, c->stream);
   cudaStreamSynchronize(c->stream);
@@ -231,7 +242,7 @@ int launch_pack(rdc_ctx* c, const double* x, int ncomp);  // solver.cu
 // fills the ghost part of x (nv values per node) from the owning ranks
 int halo_exchange(rdc_ctx* c, double* x, bool check_done) {
   if (c->S.nranks == 1) return 0;
-  if (p2p_owns(c, x)) return p2p_launch_halo(c, x, check_done);
+  if (p2p_on(c)) return p2p_launch_halo(c, x, check_done);   // any device vector: only the staging areas are peer-mapped
   const int nv = c->nv;
   int rc = launch_pack(c, x, nv);
   if (rc) return rc;
@@ -251,7 +262,6 @@ int halo_exchange(rdc_ctx* c, double* x, bool check_done) {
 int allreduce_sum(rdc_ctx* c, double* d_buf, int n, bool check_done) {
   if (c->S.nranks == 1 || n == 0) return 0;
   if (c->p2p && c->p2p->on && n <= 8) return p2p_launch_allreduce(c, d_buf, n, check_done);
-  if (c->p2p) c->p2p->dirty = false;  // an NCCL all-reduce orders the ranks just as well
   RDC_NCCL(c->nccl->AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
   return 0;
 }

@@ -43,11 +43,10 @@ struct P2P {
   int nslots = 0, slots_used = 0;
   std::vector<void*> peer;               // [nranks] mapped arena base of every rank (own arena for self)
   void** d_peer = nullptr;
-  std::vector<int64_t> dst_node_off;     // per neighbour: local node offset of MY segment in ITS ghost tail
-  unsigned* d_counter = nullptr;         // per neighbour block counters
+  std::vector<int64_t> dst_node_off;     // per neighbour: offset (nodes) of MY segment in ITS ghost ordering
+  size_t stage_off[2] = {0, 0};          // arena offsets of the two ghost staging areas (16 B per value)
   double* d_scratch = nullptr;
   unsigned long long halo_seq = 0, ar_seq = 0;
-  bool dirty = false;                    // an exchange happened since the last all-reduce
 };
 
 // Host-side result of the one-time set-up (partition, numbering, pattern, assembly maps).
@@ -186,13 +185,13 @@ void comm_destroy(rdc_ctx* c);
 int p2p_init(rdc_ctx* c, std::string& err);        // after comm_init: arena, IPC handles, peer tables
 double* p2p_alloc(rdc_ctx* c, size_t n_doubles);   // vector slot inside the arena (nullptr: not available)
 bool p2p_owns(const rdc_ctx* c, const void* p);
+inline bool p2p_on(const rdc_ctx* c) { return c->p2p && c->p2p->on; }
 // p2p.cu
 int p2p_launch_halo(rdc_ctx* c, double* x, bool check_done);
 int p2p_launch_allreduce(rdc_ctx* c, double* d_buf, int n, bool check_done);
 int p2p_check_error(rdc_ctx* c);
 struct HaloArgs;
-void p2p_fill_halo_args(rdc_ctx* c, const double* x, HaloArgs* A, int* max_blk, int* total_blk);
-int p2p_halo_begin(rdc_ctx* c, unsigned long long* seq);
+void p2p_fill_halo_args(rdc_ctx* c, HaloArgs* A, int* max_blk, int* total_blk, unsigned long long* seq);
 }  // namespace rdc
 
 #define RDC_CUDA(call)                                                                   \

@@ -548,7 +548,6 @@ static ArCtx ar_begin(rdc_ctx* c, bool* fused) {
   a.me = c->S.rank;
   a.nranks = c->S.nranks;
   a.seq = ++P->ar_seq;
-  P->dirty = false;
   *fused = true;
   return a;
 }
@@ -1199,7 +1198,6 @@ __device__ __forceinline__ double bi_target(const double* D, double rtol) { retu
 struct HaloBundle {
   HaloArgs A;
   const int32_t* send_idx = nullptr;
-  unsigned* counter = nullptr;
   P2PHeader* hdr = nullptr;
   unsigned long long seq = 0;
   int total = 0;   // number of exchange blocks at the front of the grid (0: no exchange)
@@ -1240,14 +1238,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_p(size_t n, int it, int rn, 
     int k = 0;
     while ((int)blockIdx.x >= hb.A.blk_ptr[k + 1]) k++;
     const int nb = hb.A.nblk[k], b = (int)blockIdx.x - hb.A.blk_ptr[k];
-    const int s0 = hb.A.send_ptr[k], cnt = (hb.A.send_ptr[k + 1] - s0) * hb.nv;
-    double* dst = hb.A.dst[k];
-    for (int i = b * blockDim.x + threadIdx.x; i < cnt; i += nb * blockDim.x) {
-      const int node = i / hb.nv, a = i - node * hb.nv;
-      const size_t j = (size_t)hb.send_idx[s0 + node] * hb.nv + a;
-      dst[i] = it == 0 ? r[j] : fma(beta, fma(-omega, v[j], p_old[j]), r[j]);
-    }
-    halo_publish_and_wait(hb.A, k, nb, hb.counter, hb.hdr, hb.seq);
+    halo_exchange_block(hb.A, k, b, nb, hb.nv, hb.send_idx, p_new, hb.seq, hb.hdr, [=](size_t j) {
+      return it == 0 ? r[j] : fma(beta, fma(-omega, v[j], p_old[j]), r[j]);
+    });
     return;
   }
   const size_t first = (blockIdx.x - hb.total) * (size_t)blockDim.x + threadIdx.x, step = (size_t)(gridDim.x - hb.total) * blockDim.x;
@@ -1267,14 +1260,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_s(size_t n, int ro, const do
     int k = 0;
     while ((int)blockIdx.x >= hb.A.blk_ptr[k + 1]) k++;
     const int nb = hb.A.nblk[k], b = (int)blockIdx.x - hb.A.blk_ptr[k];
-    const int s0 = hb.A.send_ptr[k], cnt = (hb.A.send_ptr[k + 1] - s0) * hb.nv;
-    double* dst = hb.A.dst[k];
-    for (int i = b * blockDim.x + threadIdx.x; i < cnt; i += nb * blockDim.x) {
-      const int node = i / hb.nv, a = i - node * hb.nv;
-      const size_t j = (size_t)hb.send_idx[s0 + node] * hb.nv + a;
-      dst[i] = fma(-alpha, v[j], r[j]);
-    }
-    halo_publish_and_wait(hb.A, k, nb, hb.counter, hb.hdr, hb.seq);
+    halo_exchange_block(hb.A, k, b, nb, hb.nv, hb.send_idx, s, hb.seq, hb.hdr, [=](size_t j) { return fma(-alpha, v[j], r[j]); });
     return;
   }
   const size_t first = (blockIdx.x - hb.total) * (size_t)blockDim.x + threadIdx.x, step = (size_t)(gridDim.x - hb.total) * blockDim.x;
@@ -1302,17 +1288,18 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, int ro, double*
 }
 
 static bool fused_halo_ok(rdc_ctx* c, const double* x) {
-  return c->opt.p2p_fused_halo && c->S.nranks > 1 && p2p_owns(c, x) && !c->S.nbr_rank.empty();
+  (void)x;  // any device vector can be exchanged: only the staging areas live in peer memory
+  return c->opt.p2p_fused_halo && c->S.nranks > 1 && p2p_on(c) && !c->S.nbr_rank.empty();
 }
 // describe the exchange of arena vector x for a fused vector kernel (bookkeeping as in p2p_launch_halo)
 static int halo_bundle(rdc_ctx* c, const double* x, HaloBundle* hb) {
+  (void)x;
   int max_blk = 1;
-  p2p_fill_halo_args(c, x, &hb->A, &max_blk, &hb->total);
+  p2p_fill_halo_args(c, &hb->A, &max_blk, &hb->total, &hb->seq);
   hb->send_idx = c->d_send_idx;
-  hb->counter = c->p2p->d_counter;
   hb->hdr = (P2PHeader*)c->p2p->arena;
   hb->nv = c->nv;
-  return p2p_halo_begin(c, &hb->seq);
+  return 0;
 }
 
 // RDC_TRACE=1: event-bracket every operation of BiCGStab iteration 4 and print the device time of each (debug aid)
