@@ -8,13 +8,15 @@ active) on the synthetic unit-cube Kuhn-tet mesh n=119 -> 10 110 954 tets, 1 728
 dt = 0.05.  One "step" = one pass of the time-loop body adpm.C:63-76: rotate time levels, assemble K and F,
 Krylov solve (BiCGStab + Jacobi by default, --ksp 0 = libMesh's GMRES(30)) to rtol 1e-12, check_solution.
   * value : device-resident steps/s (inputs in HBM when the timed region starts), CUDA events, max over ranks
-  * e2e   : the same step through the C ABI with HOST buffers every step: rdc_set_solution (pinned H2D) ->
-            rdc_step -> rdc_get_solution (D2H)
+  * e2e   : the SAME steps (state restored in between) through the C ABI with HOST buffers every step:
+            rdc_set_solution (pinned H2D) -> rdc_step -> rdc_get_solution_owned (D2H; distributed: every rank moves
+            its own dofs only)
   * roofline : the dominant kernel (block-CSR SpMV): algorithmic bytes / mean launch time, timed live with an
             event pair around every SpMV launch of the timed steps; assembly reported next to it
   * cpu_baseline : the CPU oracle (port of the reference path: element loop + scalar CSR + GMRES(30) +
             block-Jacobi/ILU(0)) on the box's host cores, on a bounded sample mesh, scaled per element
-N > 1 (torchrun): strong scaling of the same mesh, METIS node partition, NCCL halo exchange + all-reduce.
+N > 1 (torchrun): strong scaling of the same mesh, METIS node partition, ghost exchange + all-reduce over NVLink
+peer memory inside the Krylov kernels (NCCL for set-up and as fallback).  --model pihna: secondary 5-species case.
 --impl reference: times the CPU port only (the real rdcFEs binary needs libMesh/PETSc/MPI: not installable).
 """
 import argparse
@@ -83,9 +85,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def workload(n):
+def workload(n, model="adpm"):
+    """(conn, xyz, params, u0, tract vectors or None) of the synthetic case; "adpm" is the BASELINE.json workload,
+    "pihna" (SURVEY 8d case S2: run/PIHNA/input.dat parameters, 5 species) is a secondary measurement."""
     from rdcfes_b200 import synth
     conn, xyz = synth.kuhn_cube(n)
+    if model == "pihna":
+        import cases
+        p, u0, ef, nf = cases.case(cases.PIHNA, conn, xyz, "full")
+        return conn, xyz, p, u0, None
     u0, tracts = synth.adpm_fields(conn, xyz, smooth=True)
     return conn, xyz, synth.adpm_params("full"), u0, tracts
 
@@ -137,6 +145,8 @@ def main():
     ap.add_argument("--ksp", type=int, default=2, help="0 GMRES(30) (libMesh default), 1 CG, 2 BiCGStab; all Jacobi, rtol 1e-12")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partitioner", type=int, default=0)
+    ap.add_argument("--model", default="adpm", choices=["adpm", "pihna"],
+                    help="adpm = the BASELINE.json workload; pihna = secondary 5-species measurement (no CPU baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -161,16 +171,19 @@ def main():
         uid = bytes(buf.cpu().numpy().tobytes())
 
     t_setup0 = time.perf_counter()
-    conn, xyz, params, u0, tracts = workload(args.n)
+    conn, xyz, params, u0, tracts = workload(args.n, args.model)
     N, E = xyz.shape[0], conn.shape[0]
-    sysm = rs.TransientRdcSystem(rs.ADPM, rs.TET4, conn, xyz, device=local, rank=rank, nranks=world,
-                                 partitioner=args.partitioner, unique_id=uid)
+    nv = 3 if args.model == "adpm" else 5
+    dt = DT if args.model == "adpm" else 0.1
+    sysm = rs.TransientRdcSystem(rs.ADPM if args.model == "adpm" else rs.PIHNA, rs.TET4, conn, xyz, device=local,
+                                 rank=rank, nranks=world, partitioner=args.partitioner, unique_id=uid)
     sysm.set_parameters(params)
-    sysm.set_elem_field(tracts)
+    if tracts is not None:
+        sysm.set_elem_field(tracts)
     sysm.ksp = args.ksp
     stream = torch.cuda.current_stream()
     sysm.set_stream(stream.cuda_stream)  # torch.cuda.Event on this stream brackets the library's kernels
-    u_host = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    u_host = torch.empty(nv * N, dtype=torch.float64).pin_memory()
     u_np = u_host.numpy()
     u_np[:] = u0.ravel()
     sysm.set_solution(u_np)
@@ -183,7 +196,10 @@ def main():
 
     # ---------------------------------------------------------------- device-resident steps ("value")
     for _ in range(args.warmup):
-        sysm.step(DT)
+        sysm.step(dt)
+    # value and e2e time the SAME steps: the state after the warm-up is kept and restored in between
+    u_start = sysm.get_solution().copy()
+    t_start = sysm.time
     acc = {"its": 0, "ms_asm": 0.0, "ms_solve": 0.0, "ms_clamp": 0.0, "ms_spmv": 0.0, "n_spmv": 0}
     launches0 = sysm.stats().kernel_launches
     sampler = ClockSampler(local)
@@ -193,7 +209,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        its, _ = sysm.step(DT)
+        its, _ = sysm.step(dt)
         st = sysm.stats()
         acc["its"] += its; acc["ms_asm"] += st.ms_assemble; acc["ms_solve"] += st.ms_solve
         acc["ms_clamp"] += st.ms_clamp; acc["ms_spmv"] += st.ms_spmv_total; acc["n_spmv"] += st.n_spmv
@@ -209,13 +225,15 @@ def main():
     steps_per_s = args.steps / (ms * 1e-3)
 
     # ---------------------------------------------------------------- end to end through host buffers
-    e2e_steps = max(3, min(args.steps, 5))
-    sysm.get_solution(u_np)              # the host copy of the CURRENT state (untimed), then the timed e2e steps
+    e2e_steps = args.steps
+    u_np[:] = u_start                    # back to the state the value steps started from (untimed)
+    sysm.set_solution(u_np)
+    sysm.time = t_start
     barrier()
     e0.record(stream)
     for _ in range(e2e_steps):
         sysm.set_solution(u_np)          # H2D of the step's input (pinned)
-        sysm.step(DT)
+        sysm.step(dt)
         sysm.get_solution_owned(u_np)    # D2H of the step's result (distributed: every rank reads back its own dofs)
     e1.record(stream)
     barrier()
@@ -238,29 +256,30 @@ def main():
     asm_ms = acc["ms_asm"] / args.steps
     asm_gbs = st.bytes_assemble / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else 0.0
     out = {
-        "metric": METRIC, "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if args.model == "adpm" else "rdc_time_steps_per_s_10Mtet_pihna", "value": steps_per_s, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"S1 ADPM P-full, unit-cube Kuhn tets n={args.n} ({E} tets, {N} nodes, {3 * N} dofs), "
-                               f"dt={DT}, {('GMRES(30)', 'CG', 'BiCGStab')[args.ksp]}+Jacobi rtol 1e-12",
-                   "parallelism": f"node partition x{world} (METIS), NCCL halo + allreduce" if world > 1 else "single GPU",
-                   "l2": "operator (1.9 GB) and vectors far exceed the 126 MB L2; no flush needed between steps",
+        "config": {"workload": (f"S1 ADPM P-full" if args.model == "adpm" else "S2 PIHNA (run/PIHNA parameters + c/h transport)") +
+                               f", unit-cube Kuhn tets n={args.n} ({E} tets, {N} nodes, {nv * N} dofs), "
+                               f"dt={dt}, {('GMRES(30)', 'CG', 'BiCGStab')[args.ksp]}+Jacobi rtol 1e-12",
+                   "parallelism": f"node partition x{world} (METIS), ghost exchange + all-reduce over NVLink peer memory" if world > 1 else "single GPU",
+                   "l2": f"operator ({st.nnzb_local * (7 if args.model == 'adpm' else 21) * 8 / 1e9:.2f} GB per rank) and vectors exceed the 126 MB L2; no flush needed between steps",
                    "setup_s": round(t_setup, 2)},
         "e2e": {"value": e2e_value, "unit": "steps/s",
-                "h2d_bytes_per_step": int(8 * 3 * (st.n_nodes_local + st.n_nodes_ghost) if world > 1 else 8 * 3 * N),
-                "d2h_bytes_per_step": int(8 * 3 * st.n_nodes_local if world > 1 else 8 * 3 * N),
+                "h2d_bytes_per_step": int(8 * nv * (st.n_nodes_local + st.n_nodes_ghost) if world > 1 else 8 * nv * N),
+                "d2h_bytes_per_step": int(8 * nv * st.n_nodes_local if world > 1 else 8 * nv * N),
                 "per": "rank" if world > 1 else "job", "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "k_spmv_tma<3,KMASK_ADPM,*,2> (row-local block-CSR SpMV, TMA-staged, fused Jacobi scaling "
+        "roofline": {"kernel": ("k_spmv_tma<3,KMASK_ADPM,*,2>" if args.model == "adpm" else "k_spmv_tma<5,KMASK_PIHNA,*,2>") + " (row-local block-CSR SpMV, TMA-staged, fused Jacobi scaling "
                                "and BiCGStab dot products)", "bound": "hbm",
                      "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
                      # workload on one GPU (profiles/r1d_spmv_tma_full.csv); other sizes were not captured
-                     "traffic": 1.673e9 if (args.n == 119 and world == 1) else None,
+                     "traffic": 1.673e9 if (args.n == 119 and world == 1 and args.model == "adpm") else None,
                      "peak_source": peak_src, "bytes_per_launch": int(st.bytes_spmv), "ms_per_launch": spmv_ms,
                      "launches_timed": acc["n_spmv"], "frac_of_nominal_8TBs": spmv_gbs / 8000.0},
-        "roofline_assembly": {"kernel": "k_assemble<Adpm,4,128,4> (fp64-pipe bound, see DESIGN.md 4.1)", "bound": "hbm", "achieved": asm_gbs, "peak": peak,
+        "roofline_assembly": {"kernel": ("k_assemble<Adpm,4,128,4>" if args.model == "adpm" else "k_assemble<Pihna,4,128,2>") + " (fp64-pipe bound, see DESIGN.md 4.1)", "bound": "hbm", "achieved": asm_gbs, "peak": peak,
                               "unit": "GB/s", "frac": asm_gbs / peak, "bytes_per_launch": int(st.bytes_assemble),
                               "index_bytes_per_launch": int(st.bytes_index), "ms_per_launch": asm_ms},
         "phases_ms_per_step": {"assemble": asm_ms, "solve": acc["ms_solve"] / args.steps,
@@ -270,7 +289,7 @@ def main():
     sysm.close()
     if world > 1:
         dist.destroy_process_group()
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.model == "adpm" and world == 1:  # reported at N = 1 only
         ncores = os.cpu_count() or 1
         sec, Es, its, ta, ts = cpu_port_run(args.cpu_n, 2, 1, ncores)
         val = 1.0 / (sec * E / Es)
