@@ -11,6 +11,8 @@ import pytest
 import cases
 from oracle import oracle as O
 
+HERE = os.path.dirname(os.path.abspath(__file__))
+
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -85,3 +87,29 @@ def test_input_dat_parsing_of_the_shipped_cases():
     np.testing.assert_array_equal(p, cases.synth.pihna_params("ref"))
     p, _ = cases.P.params_from_input(cases.RIPF, f"{base}/RIPF133/input.dat")
     np.testing.assert_array_equal(p, cases.synth.ripf_params("ref"))
+
+
+# ---- the two meshes the reference ships (fixtures made by tests/golden/make_mesh_fixtures.py) ----
+def _pins(pr, dt, O):
+    pr.u_old = pr.u.copy()
+    val, rhs = pr.assemble(dt, dt)
+    pr.time = 0.0
+    pr.step(dt, pc=O.PC_ILU)
+    w = np.cos(np.arange(val.size) * 0.37)
+    return np.array([val.sum(), (val * w).sum(), np.abs(val).max(), rhs.sum(), np.linalg.norm(pr.u), pr.u.sum()])
+
+
+@pytest.mark.parametrize("name,etype", [("hydrogel_tet4", 4), ("cube_hex8", 8)])
+def test_oracle_on_the_shipped_meshes(name, etype):
+    """Unstructured TET4 (5 504 elements, valence up to 40) and the HEX8 cube of run/Solid: the oracle's operator
+    checksums and one-step solutions are pinned."""
+    import cases
+    from oracle import oracle as O
+    d = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    conn, xyz = d["conn"], d["xyz"]
+    for model in (cases.ADPM, cases.PIHNA, cases.HCC):
+        p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+        pr = cases.oracle_problem(model, etype, conn, xyz, p, u0, ef, nf)
+        got = _pins(pr, cases.DT[model], O)
+        ref = d["pin_" + cases.NAMES[model]]
+        assert np.allclose(got, ref, rtol=1e-10, atol=0), (cases.NAMES[model], got, ref)

@@ -324,3 +324,36 @@ def test_full_size_properties(n):
     print(f"n={n}: its {its}, assemble {st.ms_assemble:.3f} ms, solve {st.ms_solve:.2f} ms")
     assert 0 < its < 500 and (u1 >= 0).all()
     gpu.close()
+
+
+# ---- the two meshes the reference ships (tests/golden/make_mesh_fixtures.py) ----
+@pytest.mark.parametrize("name,etype", [("hydrogel_tet4", TET4), ("cube_hex8", HEX8)])
+@pytest.mark.parametrize("model", [ADPM, PIHNA, HCC])
+def test_shipped_meshes(name, etype, model):
+    """run/Solid/hydrogel_tension/hydrogel_model.msh (unstructured TET4, node valence up to 58 elements, rows of 4 to
+    ~30 blocks) and run/Solid/uniaxial_compression/cube.msh (HEX8): operator and one step against the oracle, and the
+    oracle's pinned checksums."""
+    import os
+    from oracle import oracle as O
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    conn, xyz = d["conn"], d["xyz"]
+    p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+    orc = cases.oracle_problem(model, etype, conn, xyz, p, u0, ef, nf)
+    gpu = cases.gpu_system(model, etype, conn, xyz, p, u0, ef, nf)
+    dt = cases.DT[model]
+    rel = _compare_operator(orc, gpu, None, dt, dt)
+    rows, rowptr, col, val, rhs = gpu.download_csr()
+    pin = d["pin_" + cases.NAMES[model]]
+    w = np.cos(np.arange(val.size) * 0.37)
+    assert np.allclose([val.sum(), (val * w).sum(), np.abs(val).max(), rhs.sum()], pin[:4], rtol=1e-10, atol=0)
+    gpu.time = 0.0
+    orc.time = 0.0
+    orc.step(dt, pc=O.PC_ILU)
+    for ksp in (2,):
+        gpu.ksp = ksp
+        gpu.step(dt)
+    u = gpu.get_solution()
+    assert np.linalg.norm(u - orc.u) <= 1e-8 * np.linalg.norm(orc.u)
+    assert np.allclose([np.linalg.norm(u), u.sum()], pin[4:], rtol=1e-8, atol=0)
+    print(f"{name} {cases.NAMES[model]}: max relative entry error {rel:.2e}")
+    gpu.close()
