@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   __shared__ int s_n2e[PAIRS + 1];
   __shared__ int s_diag[PAIRS];
   __shared__ int s_cptr[PAIRS * NEN + 1];            // contributor offsets of the CTA's blocks (relative)
-  __shared__ unsigned short s_clist[PAIRS * NEN];    // contributor codes j*PAIRS + pair = offset inside a stage slot
+  __shared__ __align__(4) unsigned short s_clist_raw[PAIRS * NEN + 4];  // contributor codes j*PAIRS + pair (offset in a stage slot)
 
   const int tid = threadIdx.x;
   // one 32-byte descriptor per CTA: a single load level instead of the chain cta_node -> n2e_ptr -> rowptr -> cptr
@@ -143,14 +143,24 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   const int4 d1 = reinterpret_cast<const int4*>(A.cta_node)[2 * (size_t)blockIdx.x + 1];
   const int node0 = d0.x, nnode = d0.y, pair0 = d0.z, npairs = d0.w;
   const int blk0 = d1.x, nblk = d1.y;
-  // index prologue: everything phase 2 needs goes to shared memory now, so its loads overlap phase 1
-  for (int r = tid; r <= nnode; r += PAIRS) { s_rowptr[r] = A.rowptr[node0 + r]; s_n2e[r] = A.n2e_ptr[node0 + r] - pair0; }
-  for (int r = tid; r < nnode; r += PAIRS) s_diag[r] = A.diag_blk[node0 + r];
+  // Index prologue: everything phase 2 needs goes to shared memory with cp.async (LDGSTS), i.e. without passing
+  // through registers -- the warps do not wait for these loads before they start phase 1 (the plain load+store
+  // version accounted for 18 % of the kernel's stall samples).  Raw values are stored; the CTA-relative offsets
+  // (pair0, c_base) are subtracted where they are used.  The uint16 contributor list is copied as 4-byte words
+  // from the aligned-down address.
+  const int c_base = d1.z;
+  const unsigned short* s_clist = s_clist_raw + (c_base & 1);
   {
-    const int c_base = d1.z;
-    for (int b = tid; b <= nblk; b += PAIRS) s_cptr[b] = A.cptr[blk0 + b] - c_base;
-    const int n_c = npairs * NEN;
-    for (int i = tid; i < n_c; i += PAIRS) s_clist[i] = A.clist[(size_t)c_base + i];
+    auto cp4 = [](void* dst, const void* src) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    for (int r = tid; r <= nnode; r += PAIRS) { cp4(&s_rowptr[r], A.rowptr + node0 + r); cp4(&s_n2e[r], A.n2e_ptr + node0 + r); }
+    for (int r = tid; r < nnode; r += PAIRS) cp4(&s_diag[r], A.diag_blk + node0 + r);
+    for (int b = tid; b <= nblk; b += PAIRS) cp4(&s_cptr[b], A.cptr + blk0 + b);
+    const int n_w = (npairs * NEN + (c_base & 1) + 1) / 2;
+    const unsigned* src_w = reinterpret_cast<const unsigned*>(A.clist + (c_base & ~1));
+    for (int i = tid; i < n_w; i += PAIRS) cp4(reinterpret_cast<unsigned*>(s_clist_raw) + i, src_w + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   // ------------------------------------------------------------------ phase 1: one pair per thread
@@ -362,6 +372,7 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
 #pragma unroll
     for (int a = 0; a < NV; a++) stageF[a * PAIRS + tid] = Facc[a];
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   // ------------------------------------------------------------------ phase 2: one block per thread
@@ -378,8 +389,8 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
     double acc[NKV > 0 ? NKV : 1];
 #pragma unroll
     for (int s = 0; s < NKV; s++) acc[s] = 0.0;
-    const int c1 = s_cptr[b + 1];
-    for (int c = s_cptr[b]; c < c1; c++) {
+    const int c1 = s_cptr[b + 1] - c_base;
+    for (int c = s_cptr[b] - c_base; c < c1; c++) {
       const double* src = stageK + s_clist[c];
 #pragma unroll
       for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * NEN * PAIRS];
@@ -394,7 +405,7 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   }
   for (int t = tid; t < nnode * NV; t += PAIRS) {
     const int r = t / NV, a = t - r * NV;
-    const int q0 = s_n2e[r], q1 = s_n2e[r + 1];
+    const int q0 = s_n2e[r] - pair0, q1 = s_n2e[r + 1] - pair0;
     double f = 0.0;
     for (int q = q0; q < q1; q++) f += stageF[a * PAIRS + q];
     A.rhs[(size_t)(node0 + r) * NV + a] = f;
