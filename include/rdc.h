@@ -204,6 +204,18 @@ int rdc_spmv(rdc_ctx*, const double* x, double* y);
 /* device-resident repetition of the SpMV kernel for the roofline measurement: returns mean ms */
 int rdc_bench_spmv(rdc_ctx*, int reps, double* mean_ms);
 
+/* ---- post-step reductions of save_solution (adpm.C:690-829, pihna.C:842-976, ripf.C:777-864) --------------------
+ * Device-side replacement of the rank-0 serial element loops behind the per-case CSV output; results are the same on
+ * every rank.  rdc_set_subdomains hands over elem->subdomain_id() renumbered 0..n_regions-1 (NULL: one region; it is
+ * the default).  A condition holds at a node when  lo <= (sum_a w[a]*u[a]) / div <= hi  (non-zero weights, ascending
+ * variable order -- c+h, (n+c+h+v)/Kappa_k, HU, cc >= min ...); an element counts when every condition holds at every
+ * one of its nodes.  rdc_region_last_mean reproduces adpm.C:780-783: the element average of variable `var` in the
+ * LAST element (element id order) of every region. */
+struct rdc_range_cond { double w[5]; double div, lo, hi; };
+int rdc_set_subdomains(rdc_ctx*, const int32_t* region /* [n_elems] or NULL */, int n_regions);
+int rdc_region_volumes(rdc_ctx*, int ncond, const struct rdc_range_cond* cond, double* vol /* [n_regions] */);
+int rdc_region_last_mean(rdc_ctx*, int var, double* mean /* [n_regions] */);
+
 /* read-only streaming probe over the stored operator values (reference point for the SpMV roofline): mean ms, bytes */
 int rdc_bench_stream(rdc_ctx*, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes);
 

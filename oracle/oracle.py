@@ -37,13 +37,49 @@ def lib():
         L = C.CDLL(build())
         L.orc_model_nvars.restype = C.c_int
         for name in ("orc_build_pattern", "orc_node_graph", "orc_assemble", "orc_element", "orc_fe_tables",
-                     "orc_ripf_check", "orc_gmres", "orc_step"):
+                     "orc_ripf_check", "orc_gmres", "orc_step", "orc_region_volumes", "orc_region_last_mean"):
             getattr(L, name).restype = C.c_int
         L.orc_free.restype = None
         L.orc_clamp_nonneg.restype = None
         L.orc_spmv.restype = None
         _LIB = L
     return _LIB
+
+
+def make_conditions(conds, nv):
+    """[(weights, div, lo, hi), ...] -> flat [ncond*8] array {w[5], div, lo, hi} (save_solution range tests)."""
+    out = np.zeros((len(conds), 8))
+    for k, (w, div, lo, hi) in enumerate(conds):
+        out[k, :nv] = w
+        out[k, 5], out[k, 6], out[k, 7] = div, lo, hi
+    return out.ravel()
+
+
+def region_volumes(elem_type, conn, xyz, u, conds, region=None, n_regions=1):
+    """save_solution thresholded volumes (adpm.C:786-812, pihna.C:885-945, ripf.C:822-847): serial reference loop."""
+    conn = np.ascontiguousarray(conn, dtype=np.int32); xyz = np.ascontiguousarray(xyz, dtype=_f64)
+    u = np.ascontiguousarray(u, dtype=_f64)
+    nv = u.size // xyz.shape[0]
+    reg = None if region is None else np.ascontiguousarray(region, dtype=np.int32)
+    c = make_conditions(conds, nv)
+    vol = np.zeros(n_regions)
+    rc = lib().orc_region_volumes(C.c_int(elem_type), C.c_int(nv), C.c_int64(xyz.shape[0]), C.c_int64(conn.shape[0]),
+                                  _p(conn), _p(xyz), _p(u), _p(reg), C.c_int(n_regions), C.c_int(len(conds)), _p(c), _p(vol))
+    assert rc == 0
+    return vol
+
+
+def region_last_mean(elem_type, conn, xyz, u, var, region=None, n_regions=1):
+    """adpm.C:763-783: element average of variable `var` in the LAST element of every region."""
+    conn = np.ascontiguousarray(conn, dtype=np.int32); xyz = np.ascontiguousarray(xyz, dtype=_f64)
+    u = np.ascontiguousarray(u, dtype=_f64)
+    nv = u.size // xyz.shape[0]
+    reg = None if region is None else np.ascontiguousarray(region, dtype=np.int32)
+    mean = np.zeros(n_regions)
+    rc = lib().orc_region_last_mean(C.c_int(elem_type), C.c_int(nv), C.c_int64(xyz.shape[0]), C.c_int64(conn.shape[0]),
+                                    _p(conn), _p(xyz), _p(u), _p(reg), C.c_int(n_regions), C.c_int(var), _p(mean))
+    assert rc == 0
+    return mean
 
 
 def nvars(model: int) -> int:

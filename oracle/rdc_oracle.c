@@ -905,6 +905,82 @@ int orc_fe_tables(int elem_type, int* nen, int* nqp, double* w, double* phi /*[n
   return 0;
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * save_solution: the per-region post-step reductions
+ *   adpm.C:690-829 (per parcellation ID: concentration of the LAST element of the region -- the reference
+ *   assigns, it does not accumulate (:780-783) -- and the volume of the elements whose nodes are all in range),
+ *   pihna.C:842-976 (four thresholded volumes, one region), ripf.C:777-864 (two volumes, two conditions per node).
+ * A condition is  lo <= (sum_a w[a] * u[a]) / div <= hi  at a node, the sum taken over the non-zero weights in
+ * ascending variable order like the reference's expressions (c+h, (n+c+h+v)/Kappa_k, HU, cc >= min ...).
+ * ---------------------------------------------------------------------------------------------- */
+/* [upstream] Tet4::volume(): triple product of the edge vectors / 6; other types: sum of JxW */
+static double elem_volume(const fe_table* T, int elem_type, const double (*X)[3]) {
+  if (elem_type == RDC_TET4) {
+    const double a[3] = {X[3][0] - X[0][0], X[3][1] - X[0][1], X[3][2] - X[0][2]};
+    const double b[3] = {X[1][0] - X[0][0], X[1][1] - X[0][1], X[1][2] - X[0][2]};
+    const double c[3] = {X[2][0] - X[0][0], X[2][1] - X[0][1], X[2][2] - X[0][2]};
+    return (a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0])) / 6.;
+  }
+  double JxW[MAXQP], dphi[MAXNEN][MAXQP][3], v = 0.0;
+  fe_reinit(T, X, JxW, dphi);
+  for (int q = 0; q < T->nqp; q++) v += JxW[q];
+  return v;
+}
+
+/* cond: ncond records of {w[5], div, lo, hi} (8 doubles).  vol[region] += Volume for the elements whose every node
+ * satisfies every condition; serial element loop in element order, exactly like the reference. */
+int orc_region_volumes(int elem_type, int nv, int64_t N, int64_t E, const int32_t* conn, const double* xyz, const double* u,
+                       const int32_t* region, int n_regions, int ncond, const double* cond, double* vol) {
+  fe_table T;
+  if (fe_table_init(&T, elem_type)) return -1;
+  (void)N;
+  for (int r = 0; r < n_regions; r++) vol[r] = 0.0;
+  for (int64_t e = 0; e < E; e++) {
+    double X[MAXNEN][3];
+    for (int l = 0; l < T.nen; l++)
+      for (int d = 0; d < 3; d++) X[l][d] = xyz[(int64_t)conn[e * T.nen + l] * 3 + d];
+    int consider = 1;
+    for (int l = 0; l < T.nen && consider; l++) {
+      const double* un = u + (int64_t)conn[e * T.nen + l] * nv;
+      for (int k = 0; k < ncond && consider; k++) {
+        const double* c = cond + 8 * k;
+        double s = 0.0;
+        int first = 1;
+        for (int a = 0; a < nv; a++)
+          if (c[a] != 0.0) { s = first ? c[a] * un[a] : s + c[a] * un[a]; first = 0; }
+        s /= c[5];
+        if (!(s >= c[6] && s <= c[7])) consider = 0;
+      }
+    }
+    if (consider) vol[region ? region[e] : 0] += elem_volume(&T, elem_type, X);
+  }
+  return 0;
+}
+
+/* mean[region] = (sum_qp JxW sum_l phi_l u_l[var]) / Volume of the LAST element of that region (adpm.C:763-783) */
+int orc_region_last_mean(int elem_type, int nv, int64_t N, int64_t E, const int32_t* conn, const double* xyz, const double* u,
+                         const int32_t* region, int n_regions, int var, double* mean) {
+  fe_table T;
+  if (fe_table_init(&T, elem_type)) return -1;
+  (void)N;
+  for (int r = 0; r < n_regions; r++) mean[r] = 0.0;
+  for (int64_t e = 0; e < E; e++) {
+    double X[MAXNEN][3], JxW[MAXQP], dphi[MAXNEN][MAXQP][3];
+    for (int l = 0; l < T.nen; l++)
+      for (int d = 0; d < 3; d++) X[l][d] = xyz[(int64_t)conn[e * T.nen + l] * 3 + d];
+    fe_reinit(&T, X, JxW, dphi);
+    double avg = 0.0;
+    for (int q = 0; q < T.nqp; q++) {
+      double val = 0.0;
+      for (int l = 0; l < T.nen; l++) val += T.phi[l][q] * u[(int64_t)conn[e * T.nen + l] * nv + var];
+      avg += JxW[q] * val;
+    }
+    mean[region ? region[e] : 0] = avg / elem_volume(&T, elem_type, X);
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * check_solution
  * ---------------------------------------------------------------------------------------------- */

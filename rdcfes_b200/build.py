@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "librdcgpu.so")
-SOURCES = ["api.cu", "assemble.cu", "solver.cu", "p2p.cu", "setup.cpp", "comm.cpp"]
+SOURCES = ["api.cu", "assemble.cu", "solver.cu", "p2p.cu", "reduce.cu", "setup.cpp", "comm.cpp"]
 HEADERS = ["rdc_internal.h", "models.cuh", "p2p_dev.cuh", os.path.join("..", "..", "include", "rdc.h")]
 
 

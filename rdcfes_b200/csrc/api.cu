@@ -240,6 +240,7 @@ extern "C" void rdc_destroy(rdc_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   solver_free(c);
+  region_free(c);
   if (p2p_owns(c, c->d_u)) c->d_u = nullptr;
   if (p2p_owns(c, c->d_td)) c->d_td = nullptr;
   comm_destroy(c);
@@ -534,6 +535,27 @@ extern "C" int rdc_bench_spmv(rdc_ctx* c, int reps, double* mean_ms) {
   *mean_ms = ms / reps;
   cudaFree(dy);
   return rc;
+}
+
+extern "C" int rdc_set_subdomains(rdc_ctx* c, const int32_t* region, int n_regions) {
+  CHECK_CTX(c);
+  return region_setup(c, region, n_regions);
+}
+
+extern "C" int rdc_region_volumes(rdc_ctx* c, int ncond, const struct rdc_range_cond* cond, double* vol) {
+  CHECK_CTX(c);
+  if (!cond || !vol) return RDC_E_ARG;
+  int rc;
+  if (!c->region && (rc = region_setup(c, nullptr, 1))) return rc;
+  return region_volumes(c, ncond, cond, vol);
+}
+
+extern "C" int rdc_region_last_mean(rdc_ctx* c, int var, double* mean) {
+  CHECK_CTX(c);
+  if (!mean) return RDC_E_ARG;
+  int rc;
+  if (!c->region && (rc = region_setup(c, nullptr, 1))) return rc;
+  return region_last_mean(c, var, mean);
 }
 
 extern "C" int rdc_bench_stream(rdc_ctx* c, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes) {

@@ -83,6 +83,7 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
 }  // namespace rdc
 
 struct SolverWork;  // solver.cu
+struct RegionWork;  // reduce.cu
 
 // Tuning switches of one context.  Defaults come from the environment (RDC_<NAME> upper case) at rdc_create and
 // can be changed with rdc_set_option; the parity tests use them to run the alternative kernels side by side.
@@ -141,6 +142,7 @@ struct rdc_ctx {
 
   // solver
   SolverWork* work = nullptr;
+  RegionWork* region = nullptr;      // save_solution reductions (rdc_set_subdomains)
 
   // comm
   rdc::P2P* p2p = nullptr;
@@ -178,6 +180,11 @@ int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob);    // o
 int halo_exchange(rdc_ctx* c, double* x, bool check_done = false);          // fills the ghost part of x
 int allreduce_sum(rdc_ctx* c, double* d_buf, int n, bool check_done = false);
 int allreduce_max(rdc_ctx* c, double* d_buf, int n);
+// reduce.cu
+int region_setup(rdc_ctx* c, const int32_t* region, int n_regions);
+void region_free(rdc_ctx* c);
+int region_volumes(rdc_ctx* c, int ncond, const rdc_range_cond* cond, double* vol);
+int region_last_mean(rdc_ctx* c, int var, double* mean);
 // comm.cpp
 int comm_unique_id(void* out128, std::string& err);
 int comm_init(rdc_ctx* c, const void* uid, std::string& err);

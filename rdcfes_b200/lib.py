@@ -34,7 +34,8 @@ EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_dis
            "rdc_update_coords", "rdc_set_solution", "rdc_get_solution", "rdc_get_solution_owned", "rdc_get_old_solution", "rdc_n_dofs",
            "rdc_set_time", "rdc_set_dt", "rdc_rotate", "rdc_assemble", "rdc_solve", "rdc_clamp", "rdc_step",
            "rdc_spmv", "rdc_bench_spmv", "rdc_bench_stream", "rdc_download_csr", "rdc_free", "rdc_get_stats", "rdc_set_stream",
-           "rdc_version", "rdc_probe_partition", "rdc_set_option"]
+           "rdc_version", "rdc_probe_partition", "rdc_set_option", "rdc_set_subdomains", "rdc_region_volumes",
+           "rdc_region_last_mean"]
 
 
 def load():
@@ -78,7 +79,8 @@ def load():
         "rdc_bench_stream": [vp, i32, i32, C.POINTER(f64), C.POINTER(i64)],
         "rdc_download_csr": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                              C.POINTER(vp), C.POINTER(vp)],
-        "rdc_get_stats": [vp, C.POINTER(Stats)], "rdc_set_stream": [vp, vp], "rdc_set_option": [vp, C.c_char_p, i32],
+        "rdc_get_stats": [vp, C.POINTER(Stats)], "rdc_set_stream": [vp, vp], "rdc_set_option": [vp, C.c_char_p, i32], "rdc_set_subdomains": [vp, vp, i32],
+        "rdc_region_volumes": [vp, i32, vp, vp], "rdc_region_last_mean": [vp, i32, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)

@@ -162,6 +162,30 @@ class TransientRdcSystem:
         self._check(rc)
         return its.value, res.value
 
+    # ------------------------------------------------------------------ save_solution reductions
+    def set_subdomains(self, region, n_regions):
+        """elem->subdomain_id() renumbered 0..n_regions-1 (adpm.C:298-320 builds the parcellation set)."""
+        region = None if region is None else np.ascontiguousarray(region, dtype=np.int32)
+        self._n_regions = int(n_regions)
+        self._check(self._L.rdc_set_subdomains(self._h, _ptr(region), int(n_regions)))
+
+    def region_volumes(self, conds):
+        """conds = [(weights[nv], div, lo, hi), ...]; returns vol[n_regions] (adpm.C:786-812, pihna.C:885-945, ripf.C:822-847)."""
+        n_regions = getattr(self, "_n_regions", 1)
+        flat = np.zeros((len(conds), 8))
+        for k, (w, div, lo, hi) in enumerate(conds):
+            flat[k, :self.nv] = w
+            flat[k, 5], flat[k, 6], flat[k, 7] = div, lo, hi
+        vol = np.zeros(n_regions)
+        self._check(self._L.rdc_region_volumes(self._h, len(conds), _ptr(flat), _ptr(vol)))
+        return vol
+
+    def region_last_mean(self, var):
+        """adpm.C:763-783: element average of variable `var` in the last element of every region."""
+        mean = np.zeros(getattr(self, "_n_regions", 1))
+        self._check(self._L.rdc_region_last_mean(self._h, int(var), _ptr(mean)))
+        return mean
+
     # ------------------------------------------------------------------ parity / measurement
     def spmv(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -68,6 +68,21 @@ def main():
         if rank == 0:
             print("   trace (gpu its, oracle its, rel err):", trace, flush=True)
         u = gpu.get_solution()
+        # save_solution reductions: every element is counted by exactly one rank, the result is the same on all ranks
+        nreg = 5
+        region = np.random.default_rng(11).integers(0, nreg, conn.shape[0]).astype(np.int32)
+        gpu.set_subdomains(region, nreg)
+        nv = cases.P.NVARS[model]
+        w = [0.0] * nv
+        w[1] = 1.0
+        conds = [(w, 1.0, float(np.quantile(u.reshape(-1, nv)[:, 1], 0.4)), 1e300)]
+        vol_ref = O.region_volumes(cases.TET4, conn, xyz, u, conds, region, nreg)
+        mean_ref = O.region_last_mean(cases.TET4, conn, xyz, u, 1, region, nreg)
+        vol = gpu.region_volumes(conds)
+        mean = gpu.region_last_mean(1)
+        if np.abs(vol - vol_ref).max() > 1e-12 * max(np.abs(vol_ref).max(), 1e-300) or \
+                np.abs(mean - mean_ref).max() > 1e-12 * max(np.abs(mean_ref).max(), 1e-300):
+            failures.append(f"{cases.NAMES[model]}: region reductions differ on rank {rank}: {vol} {vol_ref} {mean} {mean_ref}")
         # owned-only download: the ranks' pieces are disjoint and together give the gathered vector; the pinned
         # buffer takes the zero-copy path, the pageable one the staged path
         pinned = torch.full((gpu.n_dofs,), float("nan"), dtype=torch.float64).pin_memory()

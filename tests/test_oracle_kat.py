@@ -350,3 +350,37 @@ def test_gmsh_reader_on_shipped_meshes():
     assert et == O.TET4 and conn.shape == (5504, 4) and xyz.shape == (1569, 3)
     X = xyz[conn]
     assert (np.linalg.det(X[:, 1:] - X[:, :1]) > 0).all()  # libMesh needs positive Jacobians
+
+
+# ---- save_solution reductions (oracle restatement of adpm.C:690-829 / pihna.C:842-976 / ripf.C:777-864) ----
+def test_region_reductions_known_answers():
+    import cases
+    conn, xyz = cases.mesh(cases.TET4, 5, distort=0.2)
+    N, E = xyz.shape[0], conn.shape[0]
+    u = np.zeros((N, 3))
+    u[:, 0] = 2.0 + 3.0 * xyz[:, 0] - xyz[:, 1] + 0.5 * xyz[:, 2]       # linear field
+    u[:, 1] = (xyz[:, 0] > 0.5).astype(float)
+    region = (np.arange(E) % 4).astype(np.int32)
+    # open range: every element counts, region volumes add up to the mesh volume, each equals the sum of its tets
+    vol = O.region_volumes(4, conn, xyz, u, [([1, 0, 0], 1.0, -1e300, 1e300)], region, 4)
+    a, b, c, d = (xyz[conn[:, k]] for k in range(4))
+    tet = np.einsum("ij,ij->i", np.cross(b - a, c - a), d - a) / 6.0
+    assert abs(vol.sum() - 1.0) < 1e-13
+    for r in range(4):
+        assert abs(vol[r] - tet[region == r].sum()) < 1e-13
+    # a range test is an AND over the nodes of an element and over the conditions
+    inside = np.all(u[conn, 1] >= 0.5, axis=1)
+    vol1 = O.region_volumes(4, conn, xyz, u, [([0, 1, 0], 1.0, 0.5, 1e300)])
+    assert abs(vol1[0] - tet[inside].sum()) < 1e-13
+    both = inside & np.all(u[conn, 0] <= 4.0, axis=1)
+    vol2 = O.region_volumes(4, conn, xyz, u, [([0, 1, 0], 1.0, 0.5, 1e300), ([1, 0, 0], 1.0, -1e300, 4.0)])
+    assert abs(vol2[0] - tet[both].sum()) < 1e-13
+    # the element average of a linear field is its value at the centroid; the LAST element of a region wins
+    mean = O.region_last_mean(4, conn, xyz, u, 0, region, 4)
+    for r in range(4):
+        e = np.nonzero(region == r)[0][-1]
+        assert abs(mean[r] - u[conn[e], 0].mean()) < 1e-12
+    # HEX8: volumes from the 2x2x2 rule
+    conn8, xyz8 = cases.mesh(cases.HEX8, 4, distort=0.2)
+    v8 = O.region_volumes(8, conn8, xyz8, np.ones((xyz8.shape[0], 3)), [([1, 0, 0], 1.0, 0.0, 2.0)])
+    assert abs(v8[0] - 1.0) < 1e-13
