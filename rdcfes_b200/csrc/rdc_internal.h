@@ -28,7 +28,6 @@ struct NcclApi;  // comm.cpp
 // ---- NVLink peer-memory exchange (p2p.cu, comm.cpp) ----
 #define RDC_MAX_RANKS 16
 struct P2PHeader {                       // at offset 0 of every rank's arena; written by the peers
-  unsigned long long halo_flag[RDC_MAX_RANKS];
   unsigned long long ar_flag[2][RDC_MAX_RANKS];
   double ar_val[2][RDC_MAX_RANKS][8];
   // all-reduce fused into the producing kernel: one double = two 8-byte words {32 data bits | 32-bit tag}, so data

@@ -9,9 +9,10 @@
 // ||B r|| <= max(rtol ||B b||, 1e-50), initial guess = current solution.
 //
 // Everything stays on the device: dot products are warp-shuffle + fixed-order block/grid reductions
-// (bit-reproducible), the Hessenberg/Givens update is a one-thread kernel, and every kernel of an
-// iteration returns immediately once the device-side "converged" flag is set, so the host only polls
-// that flag every few iterations instead of synchronising per dot product.
+// (bit-reproducible) fused into the kernels that produce their operands, the Hessenberg/Givens update is a
+// one-thread kernel, and every kernel of an iteration returns immediately once the device-side "converged"
+// flag is set; the host learns about convergence a few iterations late from pinned memory (BiCGStab) or by
+// polling every few iterations (GMRES, CG).  A BiCGStab breakdown falls back to GMRES from the current iterate.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -24,8 +25,6 @@ namespace rdc {
 
 static constexpr int RED_BLOCKS = 592;   // 4 CTAs per SM on 148 SMs
 static constexpr int RED_THREADS = 256;
-static constexpr int MD_CHUNK = 8;       // vectors per multi-dot pass
-static constexpr int SPMV_SUB = 1024;    // rows whose row pointers one SpMV CTA stages in shared memory at a time
 static constexpr int SPMV_MAX_GRID = 148 * 32;
 
 }  // namespace rdc
@@ -41,7 +40,7 @@ struct SolverWork {
   double* t4 = nullptr;
   double* hs = nullptr;      // BiCGStab s (exchanged)
   double* hp2 = nullptr;     // second p buffer (exchanged)
-  double* partial = nullptr; // [RED_BLOCKS * (MD_CHUNK+1)]
+  double* partial = nullptr; // per-block partials of the fixed-order reductions
   unsigned* counter = nullptr;
   double* h = nullptr;       // [restart_cap + 2] dots of the current column (+ norm^2)
   double* H = nullptr;       // [(restart_cap+1) * restart_cap] column-major Hessenberg after rotations
@@ -55,7 +54,6 @@ struct SolverWork {
   int n_ev_used = 0;
   bool spmv_time_pending = false;
   static constexpr int RING = 8;
-  cudaEvent_t ev_ring[RING];
   int* h_ring = nullptr;     // pinned copies of the convergence flag
   int4* tiles = nullptr;     // SpMV tiles {row0, nrows, first block, nblocks} (k_spmv_tma)
   int n_tiles = 0;
@@ -913,7 +911,6 @@ int solver_init(rdc_ctx* c) {
       W->n_tiles = (int)tl.size();
     }
   }
-  for (int k = 0; k < SolverWork::RING; k++) RDC_CUDA(cudaEventCreateWithFlags(&W->ev_ring[k], cudaEventDisableTiming));
   RDC_CUDA(cudaHostAlloc(&W->h_ring, sizeof(int) * SolverWork::RING, cudaHostAllocMapped));
   memset(W->h_ring, 0, sizeof(int) * SolverWork::RING);
   return 0;
@@ -962,7 +959,6 @@ void solver_free(rdc_ctx* c) {
   cudaFree(W->g); cudaFree(W->y); cudaFree(W->scal); cudaFree(W->state);
   cudaFreeHost(W->h_scal); cudaFreeHost(W->h_state);
   for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) cudaEventDestroy(W->ev[k]);
-  for (int k = 0; k < SolverWork::RING; k++) cudaEventDestroy(W->ev_ring[k]);
   cudaFreeHost(W->h_ring);
   cudaFree(W->tiles);
   delete W;
@@ -1035,7 +1031,6 @@ static int gmres(rdc_ctx* c, const double* scale, double rtol, int maxits, int m
   k_set_target<<<1, 1, 0, c->stream>>>(W->h, rtol, W->scal);
   c->st.kernel_launches++;
   int its = 0;
-  bool converged = false;
   while (true) {
     // v0 = B (b - A x)
     if ((rc = halo_exchange(c, c->d_u))) return rc;
@@ -1046,7 +1041,7 @@ static int gmres(rdc_ctx* c, const double* scale, double rtol, int maxits, int m
     k_gmres_begin<<<1, 1, 0, c->stream>>>(W->h, W->g, W->scal, W->state, m);
     c->st.kernel_launches++;
     if ((rc = poll(c))) return rc;
-    if (W->h_state[0]) { converged = true; break; }
+    if (W->h_state[0]) break;
     if (its >= maxits) break;
     k_scale_dev<<<grid_for(n), 256, 0, c->stream>>>(n, W->V, W->scal + 3, W->state);
     c->st.kernel_launches++;
@@ -1076,7 +1071,7 @@ static int gmres(rdc_ctx* c, const double* scale, double rtol, int maxits, int m
     if ((rc = poll(c))) return rc;
     its = W->h_state[1];
     if (W->h_state[3]) { c->err = "GMRES breakdown (NaN residual)"; *its_out = its; *res_out = W->h_scal[0]; return RDC_E_DIVERGED; }
-    if (W->h_state[0]) { converged = true; break; }
+    if (W->h_state[0]) break;
     if (its >= maxits) break;
     RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int), c->stream));  // keep counters, clear done
   }
@@ -1084,7 +1079,6 @@ static int gmres(rdc_ctx* c, const double* scale, double rtol, int maxits, int m
   *its_out = W->h_state[1];
   *res_out = W->h_scal[0];
   c->st.resnorm0 = W->h_scal[5];
-  (void)converged;
   return 0;
 }
 
@@ -1436,7 +1430,16 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   int rc;
   if (ksp == RDC_KSP_GMRES) rc = gmres(c, scale, rtol, maxits, restart, its, res);
   else if (ksp == RDC_KSP_CG) rc = pcg(c, scale, rtol, maxits, its, res);
-  else if (ksp == RDC_KSP_BICGSTAB) rc = bicgstab(c, scale, rtol, maxits, its, res);
+  else if (ksp == RDC_KSP_BICGSTAB) {
+    rc = bicgstab(c, scale, rtol, maxits, its, res);
+    if (rc == RDC_E_DIVERGED && *res == *res) {
+      // rho or omega vanished (not a NaN): the iterate is still valid, continue with the method that cannot break
+      // down this way; all ranks take this branch alike because the flags derive from all-reduced values
+      int its2 = 0;
+      rc = gmres(c, scale, rtol, maxits, restart, &its2, res);
+      *its += its2;
+    }
+  }
   else { c->err = "unknown ksp"; return RDC_E_ARG; }
   // The event-bracketed SpMV launches of this solve are summed lazily (solver_spmv_time) so that the solve
   // does not end with a host synchronisation.  Launches issued after convergence return at once (device-side
