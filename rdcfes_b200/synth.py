@@ -110,11 +110,11 @@ def read_gmsh(path: str):
 
 
 # ------------------------------------------------------------------------------------ parameter sets
-def adpm_params(which: str = "full") -> np.ndarray:
-    """P-ref = effective run/HCP102513/input.dat (reaction only, Appendix C-1); P-full exercises every term."""
+def adpm_param_dict(which: str = "full") -> Dict[str, float]:
+    """GetPot key -> value of the two ADPM parameter sets (what an input.dat would hold)."""
     if which == "ref":
-        return P.flat_params(P.ADPM, {"decay/PrP": 1.0e-4, "decay/PrP/pulse/0": 0.01, "decay/PrP/pulse/1": 10.0,
-                                      "decay/Tau": 10.0, "decay/Tau/pulse/0": 0.0005})
+        return {"decay/PrP": 1.0e-4, "decay/PrP/pulse/0": 0.01, "decay/PrP/pulse/1": 10.0,
+                "decay/Tau": 10.0, "decay/Tau/pulse/0": 0.0005}
     v: Dict[str, float] = {"decay/PrP": 0.1, "decay/PrP/pulse/0": 0.01, "decay/PrP/pulse/1": 10.0,
                            "decay/PrP/time_exponent": 0.5}
     for s in ("A_b", "Tau"):
@@ -122,7 +122,12 @@ def adpm_params(which: str = "full") -> np.ndarray:
                   f"produce/{s}": 0.1, f"produce/{s}/sigmoid/0": 0.5, f"produce/{s}/sigmoid/1": 0.9,
                   f"transform/{s}": 0.05, f"transform/{s}/trapezoid/0": 1e-4, f"transform/{s}/trapezoid/1": 1e-3,
                   f"transform/{s}/trapezoid/2": 1.0, f"transform/{s}/trapezoid/3": 10.0, f"decay/{s}": 0.1})
-    return P.flat_params(P.ADPM, v)
+    return v
+
+
+def adpm_params(which: str = "full") -> np.ndarray:
+    """P-ref = effective run/HCP102513/input.dat (reaction only, Appendix C-1); P-full exercises every term."""
+    return P.flat_params(P.ADPM, adpm_param_dict(which))
 
 
 def pihna_params(which: str = "ref") -> np.ndarray:

@@ -1,0 +1,89 @@
+"""The stand-alone C++ driver (driver/adpm_driver.cpp) end to end: Gmsh mesh + input.dat + field files in, the
+reference's time loop over the C ABI, save_solution CSV out -- compared with the Python mirror (same library, so the
+numbers must be identical) and with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from oracle import oracle as O
+from rdcfes_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_gmsh(path, conn, xyz, ids):
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % xyz.shape[0])
+        for k, (x, y, z) in enumerate(xyz):
+            f.write("%d %.17g %.17g %.17g\n" % (k + 1, x, y, z))
+        f.write("$EndNodes\n$Elements\n%d\n" % (conn.shape[0] + 2))
+        f.write("1 2 2 99 1 1 2 3\n2 2 2 99 1 2 3 4\n")                      # two boundary triangles: skipped
+        for e, c in enumerate(conn):
+            f.write("%d 4 2 %d %d %s\n" % (e + 3, ids[e], ids[e], " ".join(str(v + 1) for v in c)))
+        f.write("$EndElements\n")
+
+
+def test_cpp_driver_matches_python_mirror_and_oracle(tmp_path):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
+    conn, xyz = cases.mesh(cases.TET4, 6, distort=0.2)
+    u0, tracts = synth.adpm_fields(conn, xyz, smooth=True)
+    E = conn.shape[0]
+    gmsh_ids = np.array([12, 3, 7])[np.random.default_rng(4).integers(0, 3, E)]     # subdomain ids; std::set order 3,7,12
+    region = np.searchsorted(np.array([3, 7, 12]), gmsh_ids).astype(np.int32)
+    d = str(tmp_path)
+    _write_gmsh(os.path.join(d, "cube.msh"), conn, xyz, gmsh_ids)
+    np.savetxt(os.path.join(d, "nodal.dat"), u0, fmt="%.17g")
+    np.savetxt(os.path.join(d, "elemental.dat"), tracts, fmt="%.17g")
+    nsteps, dt = 4, 0.05
+    kv = synth.adpm_param_dict("full")
+    lo, hi = 0.02, 0.5
+    with open(os.path.join(d, "input.dat"), "w") as f:
+        f.write("# written by tests/test_gpu_driver.py\ninput_GMSH = 'cube.msh'\ninput_nodal = 'nodal.dat'\n"
+                "input_elemental = 'elemental.dat'\noutput_CSV = out.csv\n")
+        f.write(f"time_step_number = {nsteps}\ntime_step = {dt}\noutput_step = 2\n")
+        f.write(f"range/A_b/min = {lo}\nrange/A_b/max = {hi}\nrange/Tau/min = {lo}\nrange/Tau/max = {hi}\n")
+        for k, v in kv.items():
+            f.write(f"{k} = {v!r}\n")
+        f.write("taxis/A_b = 999.0   # ignored key, like in run/HCP102513/input.dat\n")
+    sol = os.path.join(d, "u.bin")
+    out = subprocess.run([os.path.join(ROOT, "driver", "adpm_driver"), os.path.join(d, "input.dat"), "ksp=2",
+                          "solution_out=" + sol], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    u_drv = np.fromfile(sol)
+    rows = [ln.split(",") for ln in open(os.path.join(d, "out.csv")).read().strip().splitlines()]
+    assert rows[0][0] == '"TIME"' and rows[0][1] == '"CONCENTRATION__A_b__3"' and rows[0][-1] == '"VOLUME__Tau__12"'
+    table = np.array([[float(x) for x in r] for r in rows[1:]])
+    assert table.shape == (1 + nsteps // 2, 1 + 4 * 3)
+
+    # the Python mirror drives the same library: identical numbers
+    gpu = cases.gpu_system(cases.ADPM, cases.TET4, conn, xyz, synth.adpm_params("full"), u0, tracts, None)
+    gpu.ksp = 2
+    gpu.set_subdomains(region, 3)
+
+    def line(time):
+        cA, cT = gpu.region_last_mean(1), gpu.region_last_mean(2)
+        vA = gpu.region_volumes([([0, 1, 0], 1.0, lo, hi)])
+        vT = gpu.region_volumes([([0, 0, 1], 1.0, lo, hi)])
+        return np.concatenate([[time], np.stack([cA, cT], 1).ravel(), np.stack([vA, vT], 1).ravel()])
+
+    ref = [line(0.0)]
+    orc = cases.oracle_problem(cases.ADPM, cases.TET4, conn, xyz, synth.adpm_params("full"), u0, tracts, None)
+    for t in range(1, nsteps + 1):
+        gpu.step(dt)
+        orc.step(dt, pc=O.PC_ILU)
+        if t % 2 == 0:
+            ref.append(line(gpu.time))
+    ref = np.array(ref)
+    assert np.array_equal(table, ref), np.abs(table - ref).max()
+    assert np.array_equal(u_drv, gpu.get_solution())
+    # and the oracle: solution to 1e-8, CSV quantities from the oracle's serial loops on ITS solution to 1e-6
+    assert np.linalg.norm(u_drv - orc.u) <= 1e-8 * np.linalg.norm(orc.u)
+    cA = O.region_last_mean(cases.TET4, conn, xyz, orc.u, 1, region, 3)
+    vT = O.region_volumes(cases.TET4, conn, xyz, orc.u, [([0, 0, 1], 1.0, lo, hi)], region, 3)
+    assert np.allclose(table[-1, 1:7:2], cA, rtol=1e-6)
+    assert np.allclose(table[-1, 8::2], vT, rtol=1e-6, atol=1e-12)
+    gpu.close()
