@@ -140,7 +140,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=119, help="cells per edge (119 -> 10.1 M tets)")
+    ap.add_argument("--n", "--cells", dest="n", type=int, default=119,
+                    help="cells per edge (119 -> 10.1 M tets; under torchrun spell it --cells: --n is ambiguous there)")
     ap.add_argument("--cpu-n", type=int, default=90, help="sample mesh of the CPU baseline (90 -> 4.4 M tets)")
     ap.add_argument("--ksp", type=int, default=2, help="0 GMRES(30) (libMesh default), 1 CG, 2 BiCGStab; all Jacobi, rtol 1e-12")
     ap.add_argument("--no-cpu-baseline", action="store_true")
