@@ -58,7 +58,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -69,9 +69,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Number of samples read so far: brackets the timed region inside a sampler that started earlier."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if last is not None and last > first:
+            self.rows = self.rows[first:last]       # the samples taken DURING the timed region
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -196,6 +202,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident steps ("value")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                  # started before the warm-up so that it is already delivering samples
     for _ in range(args.warmup):
         sysm.step(dt)
     # value and e2e time the SAME steps: the state after the warm-up is kept and restored in between
@@ -203,10 +212,8 @@ def main():
     t_start = sysm.time
     acc = {"its": 0, "ms_asm": 0.0, "ms_solve": 0.0, "ms_clamp": 0.0, "ms_spmv": 0.0, "n_spmv": 0}
     launches0 = sysm.stats().kernel_launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
+    mark0 = sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -217,7 +224,7 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(mark0, sampler.mark()) if rank == 0 else None
     launches = sysm.stats().kernel_launches - launches0
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")

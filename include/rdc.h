@@ -255,6 +255,12 @@ int rdc_probe_partition(int elem_type, int nvars, int64_t n_nodes, int64_t n_ele
  * "spmv_minb", "spmv_ctas_per_sm", "tma_ctas_per_sm", "tma_stages", "sync_every", "p2p_fused_ar",
  * "p2p_fused_halo", "trace".  Results do not depend on them beyond floating-point summation order. */
 int rdc_set_option(rdc_ctx*, const char* name, int value);
+/* Host-only probes of set-up logic, for CPU tests (arrays malloc'ed by the library, rdc_free): the SpMV tile cutter
+ * (tiles = n_tiles x {row0, nrows, first block, nblocks}; n_tiles = -1 when a row exceeds max_blocks) and the region
+ * bucketing of the save_solution reductions. */
+int rdc_probe_spmv_tiles(int32_t n_rows, const int32_t* rowptr, int max_rows, int max_blocks, int32_t* n_tiles, int32_t** tiles);
+int rdc_probe_region_chunks(int64_t n_elems, const uint8_t* counted, const int32_t* region, int n_regions, int chunk,
+                            int64_t* n_counted, int32_t** perm, int32_t* n_chunks, int32_t** chunk_ptr, int32_t** rchunk_ptr);
 /* run every kernel on this cudaStream_t (default: a stream owned by the context) */
 int rdc_set_stream(rdc_ctx*, void* cuda_stream);
 const char* rdc_version(void);

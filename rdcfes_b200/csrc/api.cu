@@ -642,6 +642,35 @@ extern "C" int rdc_download_csr(rdc_ctx* c, int64_t* n_rows, int64_t* nnz, int64
   return RDC_OK;
 }
 
+// Host-only probes of two pieces of set-up logic (no device needed; CPU tests check their invariants).
+extern "C" int rdc_probe_spmv_tiles(int32_t n_rows, const int32_t* rowptr, int max_rows, int max_blocks, int32_t* n_tiles,
+                                    int32_t** tiles) {
+  if (!rowptr || !n_tiles || !tiles || n_rows < 0 || max_rows < 1 || max_blocks < 1) return RDC_E_ARG;
+  std::vector<int32_t> t;
+  const bool ok = cut_spmv_tiles(rowptr, n_rows, max_rows, max_blocks, t);
+  *n_tiles = ok ? (int32_t)(t.size() / 4) : -1;
+  *tiles = (int32_t*)malloc(sizeof(int32_t) * std::max<size_t>(t.size(), 1));
+  if (!t.empty()) memcpy(*tiles, t.data(), sizeof(int32_t) * t.size());
+  return RDC_OK;
+}
+
+extern "C" int rdc_probe_region_chunks(int64_t n_elems, const uint8_t* counted, const int32_t* region, int n_regions, int chunk,
+                                       int64_t* n_counted, int32_t** perm, int32_t* n_chunks, int32_t** chunk_ptr,
+                                       int32_t** rchunk_ptr) {
+  if (!counted || !region || n_regions < 1 || chunk < 1) return RDC_E_ARG;
+  std::vector<int32_t> p, cp, rp;
+  bucket_regions(n_elems, counted, region, n_regions, chunk, p, cp, rp);
+  auto dup = [](const std::vector<int32_t>& v) {
+    int32_t* q = (int32_t*)malloc(sizeof(int32_t) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) memcpy(q, v.data(), sizeof(int32_t) * v.size());
+    return q;
+  };
+  *n_counted = (int64_t)p.size();
+  *n_chunks = (int32_t)cp.size() - 1;
+  *perm = dup(p); *chunk_ptr = dup(cp); *rchunk_ptr = dup(rp);
+  return RDC_OK;
+}
+
 // Host-only probe of the partition / halo set-up (no device needed): lets the world_size-2 gloo tests check on
 // CPU that what rank r sends is exactly what rank q expects to receive.  Buffers are malloc'ed; free with
 // rdc_free.  send_glob / recv_glob hold GLOBAL node ids, grouped per neighbour (nbr_ptr offsets).

@@ -79,6 +79,10 @@ struct HostSetup {
 int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const int32_t* conn, const double* xyz,
                 int rank, int nranks, int partitioner, int pairs_per_cta, std::string& err);
 
+bool cut_spmv_tiles(const int32_t* rowptr, int32_t n_rows, int max_rows, int max_blocks, std::vector<int32_t>& tiles);
+void bucket_regions(int64_t E_loc, const uint8_t* counted, const int32_t* region_of_local, int n_regions, int chunk,
+                    std::vector<int32_t>& perm, std::vector<int32_t>& chunk_ptr, std::vector<int32_t>& rchunk_ptr);
+
 }  // namespace rdc
 
 struct SolverWork;  // solver.cu

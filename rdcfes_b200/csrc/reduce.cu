@@ -182,23 +182,13 @@ int region_setup(rdc_ctx* c, const int32_t* region, int n_regions) {
   RegionWork* R = new RegionWork();
   c->region = R;
   R->n_regions = n_regions;
-  std::vector<int64_t> cnt((size_t)n_regions + 1, 0);
   auto reg_of = [&](int64_t le) { return region ? region[S.elem_glob[le]] : 0; };
-  for (int64_t le = 0; le < S.E_loc; le++)
-    if (first[le] < S.n_owned) cnt[reg_of(le) + 1]++;
-  for (int r = 0; r < n_regions; r++) cnt[r + 1] += cnt[r];
-  R->n_mine = cnt[n_regions];
-  std::vector<int32_t> perm((size_t)std::max<int64_t>(R->n_mine, 1));
-  {
-    std::vector<int64_t> cur(cnt.begin(), cnt.end() - 1);
-    for (int64_t le = 0; le < S.E_loc; le++)   // local element order == global element order: stable buckets
-      if (first[le] < S.n_owned) perm[cur[reg_of(le)]++] = (int32_t)le;
-  }
-  std::vector<int32_t> chunk_ptr(1, 0), rchunk_ptr((size_t)n_regions + 1, 0);
-  for (int r = 0; r < n_regions; r++) {
-    for (int64_t a = cnt[r]; a < cnt[r + 1]; a += RCHUNK) chunk_ptr.push_back((int32_t)std::min<int64_t>(a + RCHUNK, cnt[r + 1]));
-    rchunk_ptr[r + 1] = (int32_t)chunk_ptr.size() - 1;
-  }
+  std::vector<uint8_t> counted((size_t)S.E_loc);
+  std::vector<int32_t> reg_loc((size_t)S.E_loc);
+  for (int64_t le = 0; le < S.E_loc; le++) { counted[le] = first[le] < S.n_owned; reg_loc[le] = reg_of(le); }
+  std::vector<int32_t> perm, chunk_ptr, rchunk_ptr;
+  bucket_regions(S.E_loc, counted.data(), reg_loc.data(), n_regions, RCHUNK, perm, chunk_ptr, rchunk_ptr);
+  R->n_mine = (int64_t)perm.size();
   R->n_chunks = (int)chunk_ptr.size() - 1;
   // the last element (global order) of every region, when it is counted here
   std::vector<int32_t> last((size_t)n_regions, -1);

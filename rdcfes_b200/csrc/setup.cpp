@@ -349,4 +349,46 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
   return 0;
 }
 
+// ---- SpMV tiles (k_spmv_tma) --------------------------------------------------------------------
+// Consecutive block rows, at most max_rows rows and max_blocks blocks per tile: {row0, nrows, first block, nblocks}.
+// Returns false when a single row is longer than a tile (the caller keeps the LDG kernel).
+bool cut_spmv_tiles(const int32_t* rowptr, int32_t n_rows, int max_rows, int max_blocks, std::vector<int32_t>& tiles) {
+  tiles.clear();
+  tiles.reserve(((size_t)n_rows / max_rows + 16) * 4);
+  for (int32_t r = 0; r < n_rows;) {
+    int32_t e = r;
+    while (e < n_rows && e - r < max_rows && rowptr[e + 1] - rowptr[r] <= max_blocks) e++;
+    if (e == r) { tiles.clear(); return false; }
+    const int32_t t[4] = {r, e - r, rowptr[r], rowptr[e] - rowptr[r]};
+    tiles.insert(tiles.end(), t, t + 4);
+    r = e;
+  }
+  return true;
+}
+
+// ---- region buckets of the save_solution reductions (reduce.cu) -----------------------------------
+// counted[le] != 0: this rank counts local element le.  Elements are bucketed by region, element order kept inside a
+// region (stable), and every region's bucket is cut into chunks of at most `chunk` elements, so no chunk straddles
+// two regions.  perm: bucketed local element ids; chunk_ptr: [n_chunks+1] into perm; rchunk_ptr: [n_regions+1] chunk
+// range of every region.
+void bucket_regions(int64_t E_loc, const uint8_t* counted, const int32_t* region_of_local, int n_regions, int chunk,
+                    std::vector<int32_t>& perm, std::vector<int32_t>& chunk_ptr, std::vector<int32_t>& rchunk_ptr) {
+  std::vector<int64_t> cnt((size_t)n_regions + 1, 0);
+  for (int64_t le = 0; le < E_loc; le++)
+    if (counted[le]) cnt[region_of_local[le] + 1]++;
+  for (int r = 0; r < n_regions; r++) cnt[r + 1] += cnt[r];
+  perm.assign((size_t)cnt[n_regions], 0);
+  {
+    std::vector<int64_t> cur(cnt.begin(), cnt.end() - 1);
+    for (int64_t le = 0; le < E_loc; le++)
+      if (counted[le]) perm[(size_t)cur[region_of_local[le]]++] = (int32_t)le;
+  }
+  chunk_ptr.assign(1, 0);
+  rchunk_ptr.assign((size_t)n_regions + 1, 0);
+  for (int r = 0; r < n_regions; r++) {
+    for (int64_t a = cnt[r]; a < cnt[r + 1]; a += chunk) chunk_ptr.push_back((int32_t)std::min<int64_t>(a + chunk, cnt[r + 1]));
+    rchunk_ptr[r + 1] = (int32_t)chunk_ptr.size() - 1;
+  }
+}
+
 }  // namespace rdc

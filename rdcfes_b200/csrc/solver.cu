@@ -891,24 +891,14 @@ int solver_init(rdc_ctx* c) {
   RDC_CUDA(cudaMallocHost(&W->h_state, sizeof(int) * 8));
   RDC_CUDA(cudaMalloc(&W->h, sizeof(double) * 1024));
   for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) RDC_CUDA(cudaEventCreate(&W->ev[k]));
-  {  // SpMV tiles: consecutive rows, at most SPMV_TILE_ROWS rows and SPMV_CAPB blocks each
-    const std::vector<int32_t>& rp = c->S.rowptr;
-    const int32_t no = c->S.n_owned;
-    std::vector<int4> tl;
-    tl.reserve((size_t)no / SPMV_TILE_ROWS + 16);
-    bool ok = true;
-    for (int32_t r = 0; r < no;) {
-      int32_t e = r;
-      while (e < no && e - r < SPMV_TILE_ROWS && rp[e + 1] - rp[r] <= SPMV_CAPB) e++;
-      if (e == r) { ok = false; break; }   // a single row longer than a stage: keep the LDG kernel
-      tl.push_back(make_int4(r, e - r, rp[r], rp[e] - rp[r]));
-      r = e;
-    }
-    if (ok && !tl.empty()) {
-      RDC_CUDA(cudaMalloc(&W->tiles, tl.size() * sizeof(int4)));
-      RDC_CUDA(cudaMemcpyAsync(W->tiles, tl.data(), tl.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+  {  // SpMV tiles: consecutive rows, at most SPMV_TILE_ROWS rows and SPMV_CAPB blocks each (setup.cpp)
+    std::vector<int32_t> tl;
+    static_assert(sizeof(int4) == 4 * sizeof(int32_t), "tile descriptor layout");
+    if (cut_spmv_tiles(c->S.rowptr.data(), c->S.n_owned, SPMV_TILE_ROWS, SPMV_CAPB, tl) && !tl.empty()) {
+      RDC_CUDA(cudaMalloc(&W->tiles, tl.size() * sizeof(int32_t)));
+      RDC_CUDA(cudaMemcpyAsync(W->tiles, tl.data(), tl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
       RDC_CUDA(cudaStreamSynchronize(c->stream));
-      W->n_tiles = (int)tl.size();
+      W->n_tiles = (int)(tl.size() / 4);
     }
   }
   RDC_CUDA(cudaHostAlloc(&W->h_ring, sizeof(int) * SolverWork::RING, cudaHostAllocMapped));

@@ -35,7 +35,7 @@ EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_dis
            "rdc_set_time", "rdc_set_dt", "rdc_rotate", "rdc_assemble", "rdc_solve", "rdc_clamp", "rdc_step",
            "rdc_spmv", "rdc_bench_spmv", "rdc_bench_stream", "rdc_download_csr", "rdc_free", "rdc_get_stats", "rdc_set_stream",
            "rdc_version", "rdc_probe_partition", "rdc_set_option", "rdc_set_subdomains", "rdc_region_volumes",
-           "rdc_region_last_mean"]
+           "rdc_region_last_mean", "rdc_probe_spmv_tiles", "rdc_probe_region_chunks"]
 
 
 def load():

@@ -104,3 +104,75 @@ def test_halo_exchange_spmv_gloo(world, partitioner):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+# ---- host-only set-up logic probed without a device ------------------------------------------------------------
+def _probe_tiles(rowptr, max_rows=16, max_blocks=256):
+    import ctypes as C
+    from rdcfes_b200 import lib
+    L = lib.load()
+    rowptr = np.ascontiguousarray(rowptr, dtype=np.int32)
+    n, tiles = C.c_int32(), C.c_void_p()
+    rc = L.rdc_probe_spmv_tiles(C.c_int32(rowptr.size - 1), rowptr.ctypes.data_as(C.c_void_p), C.c_int(max_rows),
+                                C.c_int(max_blocks), C.byref(n), C.byref(tiles))
+    assert rc == 0
+    out = None
+    if n.value >= 0:
+        out = np.ctypeslib.as_array(C.cast(tiles, C.POINTER(C.c_int32)), shape=(max(n.value, 1) * 4,))[: n.value * 4].copy()
+        out = out.reshape(-1, 4)
+    L.rdc_free(tiles)
+    return out
+
+
+def test_spmv_tile_cutter_invariants():
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        lens = rng.integers(1, 60, size=rng.integers(1, 400))
+        if trial % 4 == 0:
+            lens[rng.integers(0, lens.size)] = 256          # a row that fills a whole tile
+        rowptr = np.concatenate([[0], np.cumsum(lens)])
+        t = _probe_tiles(rowptr)
+        assert t is not None
+        assert t[0, 0] == 0 and np.array_equal(t[1:, 0], t[:-1, 0] + t[:-1, 1]) and t[-1, 0] + t[-1, 1] == lens.size
+        assert (t[:, 1] >= 1).all() and (t[:, 1] <= 16).all() and (t[:, 3] <= 256).all()
+        assert np.array_equal(t[:, 2], rowptr[t[:, 0]]) and np.array_equal(t[:, 3], rowptr[t[:, 0] + t[:, 1]] - rowptr[t[:, 0]])
+        # greedy: a tile stops only because the next row would break a limit
+        for k in range(t.shape[0] - 1):
+            nxt = t[k, 0] + t[k, 1]
+            assert t[k, 1] == 16 or t[k, 3] + lens[nxt] > 256
+    assert _probe_tiles(np.array([0, 5, 300, 310])) is None     # one row longer than a tile: LDG kernel instead
+    assert _probe_tiles(np.array([0])).shape == (0, 4)
+
+
+def test_region_bucketing_invariants():
+    import ctypes as C
+    from rdcfes_b200 import lib
+    L = lib.load()
+    rng = np.random.default_rng(1)
+    E, nreg, chunk = 5000, 7, 256
+    counted = (rng.random(E) < 0.8).astype(np.uint8)
+    region = rng.integers(0, nreg, E).astype(np.int32)
+    region[region == 4] = 5                                   # an empty region
+    n_counted, n_chunks = C.c_int64(), C.c_int32()
+    perm, cptr, rptr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    rc = L.rdc_probe_region_chunks(C.c_int64(E), counted.ctypes.data_as(C.c_void_p), region.ctypes.data_as(C.c_void_p),
+                                   C.c_int(nreg), C.c_int(chunk), C.byref(n_counted), C.byref(perm), C.byref(n_chunks),
+                                   C.byref(cptr), C.byref(rptr))
+    assert rc == 0
+
+    def take(p, n):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(max(n, 1),))[:n].copy()
+        L.rdc_free(p)
+        return a
+
+    perm, cptr, rptr = take(perm, n_counted.value), take(cptr, n_chunks.value + 1), take(rptr, nreg + 1)
+    assert n_counted.value == counted.sum() and np.array_equal(np.sort(perm), np.nonzero(counted)[0])
+    assert np.all(np.diff(region[perm]) >= 0)                                    # bucketed by region ...
+    for r in range(nreg):
+        mine = perm[region[perm] == r]
+        assert np.all(np.diff(mine) > 0)                                         # ... element order kept inside
+    assert cptr[0] == 0 and cptr[-1] == perm.size and np.all(np.diff(cptr) >= 1) and np.all(np.diff(cptr) <= chunk)
+    assert rptr[0] == 0 and rptr[-1] == n_chunks.value and rptr[5] - rptr[4] == 0
+    for r in range(nreg):                                                        # no chunk straddles two regions
+        for c in range(rptr[r], rptr[r + 1]):
+            assert np.all(region[perm[cptr[c]:cptr[c + 1]]] == r)
