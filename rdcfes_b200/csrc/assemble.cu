@@ -429,7 +429,8 @@ template <class M, int NEN, int PAIRS, int MINB>
 static int launch_t(rdc_ctx* c, const AsmArgs& A, const typename M::Params& P) {
   constexpr unsigned KMASK = M::CMASK | M::SMASK | M::TMASK;
   const size_t smem = ((size_t)NEN * popc(KMASK) + M::NV) * PAIRS * sizeof(double);
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};   // kernel attributes are per device: a process may drive several GPUs
+  bool& attr_done = attr_done_dev[c->device & 63];
   if (!attr_done) {
     RDC_CUDA(cudaFuncSetAttribute(k_assemble<M, NEN, PAIRS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     RDC_CUDA(cudaFuncSetAttribute(k_assemble<M, NEN, PAIRS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,

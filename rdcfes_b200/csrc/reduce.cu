@@ -163,13 +163,11 @@ int region_setup(rdc_ctx* c, const int32_t* region, int n_regions) {
   region_free(c);
   const HostSetup& S = c->S;
   if (n_regions < 1) { c->err = "rdc_set_subdomains: n_regions must be positive"; return RDC_E_ARG; }
-  static bool tables_up = false;
-  if (!tables_up) {
+  {  // __constant__ memory is per device: upload on every set-up (a process may drive several GPUs)
     FeTable t[2];
     fe_table_fill(&t[0], RDC_TET4);
     fe_table_fill(&t[1], RDC_HEX8);
     RDC_CUDA(cudaMemcpyToSymbol(c_fe_red, t, sizeof(t)));
-    tables_up = true;
   }
   if (region)
     for (int64_t e = 0; e < S.E_glob; e++)

@@ -513,7 +513,10 @@ static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const
                     const double* val, const double* x, double* y, const double* rowscale, const double* w, double* y2,
                     double* partial, unsigned* counter, double* out, const int* done, const ArCtx& ar) {
   constexpr int SMEM = STAGES * SpmvStage<popc_c(KMASK)>::BYTES;
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};   // kernel attributes are per device: a process may drive several GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_done = attr_done_dev[dev & 63];
   if (!attr_done) {
     cudaError_t e = cudaSuccess;
 #define RDC_TMA_ATTR(MODE) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_spmv_tma<NV, KMASK, MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)
