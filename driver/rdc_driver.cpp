@@ -1,0 +1,286 @@
+// rdc_driver.cpp -- stand-alone C++ driver of the ADPM, PIHNA and RIPF models on top of the C ABI (include/rdc.h).
+//
+// Mirrors what rdcFEs' own drivers do around the hot path, without libMesh: adpm() / pihna() / ripf()
+// (adpm.C:15-87, pihna.C:18-96, ripf.C:13-96) read input.dat with GetPot (input()), the Gmsh mesh, the nodal and
+// elemental initial fields in node / element order (initial_adpm adpm.C:264-322, initial_tracts adpm.C:230-262,
+// initial_pihna pihna.C:272-316, initial_ripf ripf.C:297-335, initial_radiotherapy ripf.C:255-295), then loop
+//     time += dt; rotate; solve; check_solution; every output step: save_solution      (adpm.C:60-84)
+// and write the CSV of save_solution (adpm.C:690-829, pihna.C:842-976, ripf.C:777-864).  Here the loop body is
+// rdc_step and the CSV comes from rdc_region_last_mean / rdc_region_volumes.  It is the C++ counterpart of
+// rdcfes_b200/system.py: the same entry points, called from the reference's own language, and what
+// tests/test_gpu_driver.py runs end to end.  The input.dat keys and defaults come from param_tables.h, generated from
+// the same table the Python mirror uses (driver/gen_tables.py).
+//
+//   rdc_driver -m adpm|pihna|ripf <input.dat> [ksp=0|1|2] [solution_out=<file>]   (paths relative to input.dat)
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "param_tables.h"
+#include "rdc.h"
+
+static void die(const std::string& msg) {
+  fprintf(stderr, "rdc_driver: %s\n", msg.c_str());
+  exit(1);
+}
+
+// GetPot subset used by the shipped input files: `key = value`, '#' comments, optional quotes
+struct Input {
+  std::map<std::string, std::string> kv;
+  explicit Input(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) die("cannot open " + path);
+    std::string line;
+    while (std::getline(f, line)) {
+      const size_t h = line.find('#');
+      if (h != std::string::npos) line.erase(h);
+      const size_t eq = line.find('=');
+      if (eq == std::string::npos) continue;
+      auto trim = [](std::string s) {
+        const char* ws = " \t\r\n'\"";
+        const size_t a = s.find_first_not_of(ws), b = s.find_last_not_of(ws);
+        return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+      };
+      kv[trim(line.substr(0, eq))] = trim(line.substr(eq + 1));
+    }
+  }
+  double real(const std::string& k, double dflt) const {
+    auto it = kv.find(k);
+    return it == kv.end() ? dflt : atof(it->second.c_str());
+  }
+  int integer(const std::string& k, int dflt) const {
+    auto it = kv.find(k);
+    return it == kv.end() ? dflt : atoi(it->second.c_str());
+  }
+  std::string str(const std::string& k, const std::string& dflt) const {
+    auto it = kv.find(k);
+    return it == kv.end() ? dflt : it->second;
+  }
+};
+
+struct Mesh {
+  int nen = 0;
+  std::vector<double> xyz;       // [N*3]
+  std::vector<int32_t> conn;     // [E*nen], 0-based
+  std::vector<int> subdomain;    // [E] first Gmsh tag (physical id) == libMesh subdomain_id
+};
+
+// Gmsh 2.2 ASCII as written by process_mesh.C:22-83; volume elements only (4 = TET4, 5 = HEX8), file order
+static Mesh read_gmsh(const std::string& path) {
+  std::ifstream f(path);
+  if (!f) die("cannot open mesh " + path);
+  Mesh m;
+  std::string tok;
+  std::map<long, int32_t> id2idx;
+  while (f >> tok) {
+    if (tok == "$Nodes") {
+      long n;
+      f >> n;
+      m.xyz.resize((size_t)n * 3);
+      for (long k = 0; k < n; k++) {
+        long id;
+        f >> id >> m.xyz[3 * k] >> m.xyz[3 * k + 1] >> m.xyz[3 * k + 2];
+        id2idx[id] = (int32_t)k;
+      }
+    } else if (tok == "$Elements") {
+      long ne;
+      f >> ne;
+      std::string line;
+      std::getline(f, line);
+      for (long k = 0; k < ne; k++) {
+        std::getline(f, line);
+        std::istringstream ss(line);
+        long id, type, ntags;
+        ss >> id >> type >> ntags;
+        std::vector<long> tags((size_t)ntags);
+        for (auto& t : tags) ss >> t;
+        const int nen = type == 4 ? 4 : (type == 5 ? 8 : 0);
+        if (!nen) continue;
+        if (m.nen && m.nen != nen) die("mixed volume element types");
+        m.nen = nen;
+        for (int l = 0; l < nen; l++) {
+          long v;
+          ss >> v;
+          m.conn.push_back(id2idx.at(v));
+        }
+        m.subdomain.push_back(ntags > 0 ? (int)tags[0] : 0);
+      }
+    }
+  }
+  if (!m.nen) die("no TET4/HEX8 elements in " + path);
+  return m;
+}
+
+static std::vector<double> read_table(const std::string& path, size_t rows, int cols) {
+  std::ifstream f(path);
+  if (!f) die("cannot open " + path);
+  std::vector<double> v(rows * cols);
+  for (auto& x : v)
+    if (!(f >> x)) die("short field file " + path);
+  return v;
+}
+
+template <size_t NK>
+static std::vector<double> flat_params(const ParamKey (&table)[NK], const Input& in) {
+  std::vector<double> p(NK);
+  for (size_t k = 0; k < NK; k++) {
+    double v = in.real(table[k].key, table[k].dflt);
+    if (table[k].degrees) v *= M_PI / 180.0;   // utils.h:79 degrees_to_radians (adpm.C:192,212)
+    p[k] = v;
+  }
+  return p;
+}
+
+int main(int argc, char** argv) {
+  std::string model_name = "adpm", in_path, sol_out;
+  int ksp = RDC_KSP_BICGSTAB;
+  for (int a = 1; a < argc; a++) {
+    if (!strcmp(argv[a], "-m") && a + 1 < argc) model_name = argv[++a];
+    else if (!strncmp(argv[a], "ksp=", 4)) ksp = atoi(argv[a] + 4);
+    else if (!strncmp(argv[a], "solution_out=", 13)) sol_out = argv[a] + 13;
+    else in_path = argv[a];
+  }
+  if (in_path.empty()) die("usage: rdc_driver -m adpm|pihna|ripf <input.dat> [ksp=2] [solution_out=file]");
+  const int model = model_name == "adpm" ? RDC_ADPM : model_name == "pihna" ? RDC_PIHNA : model_name == "ripf" ? RDC_RIPF : -1;
+  if (model < 0) die("unknown model " + model_name + " (main.C:24-38 knows adpm, pihna, proteas, ripf)");
+  const int nv = rdc_model_nvars(model);
+  const size_t slash = in_path.find_last_of('/');
+  const std::string dir = slash == std::string::npos ? std::string() : in_path.substr(0, slash + 1);
+  Input in(in_path);
+
+  // ---- es.parameters, with the defaults of the model's input() --------------------------------------------------
+  std::vector<double> p;
+  if (model == RDC_ADPM) p = flat_params(kAdpmTable, in);
+  else if (model == RDC_PIHNA) p = flat_params(kPihnaTable, in);
+  else {
+    p = flat_params(kRipfTable, in);
+    if (!in.kv.count("volume_fraction/max_vacant")) p[RIPF_VF_MAX_VACANT] = 1.0 - p[RIPF_VF_MIN_VACANT];   // ripf.C:181-182
+  }
+  if ((int)p.size() != rdc_model_nparams(model)) die("parameter table out of date: run driver/gen_tables.py");
+  const double dt = in.real("time_step", 1.0e-9);
+  const int n_steps = in.integer("time_step_number", 1);
+  const int out_step = in.integer("output_step", 0);
+
+  // ---- mesh and initial fields ---------------------------------------------------------------------------------
+  Mesh mesh = read_gmsh(dir + in.str("input_GMSH", "input.msh"));
+  const int64_t N = (int64_t)mesh.xyz.size() / 3, E = (int64_t)mesh.conn.size() / mesh.nen;
+  std::vector<double> u0 = read_table(dir + in.str("input_nodal", "input.nodal"), (size_t)N, nv);
+  std::set<int> parcellation(mesh.subdomain.begin(), mesh.subdomain.end());   // adpm.C:302-310 (std::set: ascending)
+  std::map<int, int> reg_of;
+  for (int id : parcellation) reg_of.emplace(id, (int)reg_of.size());
+  std::vector<int32_t> region((size_t)E);
+  for (int64_t e = 0; e < E; e++) region[e] = reg_of[mesh.subdomain[e]];
+  const int n_regions = model == RDC_ADPM ? (int)parcellation.size() : 1;   // only ADPM reports per region
+
+  // ---- hand-over (once) -------------------------------------------------------------------------------------------
+  rdc_ctx* ctx = nullptr;
+  auto ck = [&](int rc, const char* what) {
+    if (rc) die(std::string(what) + ": " + rdc_last_error(ctx));
+  };
+  ck(rdc_create(&ctx, model, mesh.nen, N, E, mesh.conn.data(), mesh.xyz.data(), nullptr, -1), "rdc_create");
+  ck(rdc_set_params(ctx, p.data(), (int)p.size()), "rdc_set_params");
+  if (model == RDC_ADPM) {
+    std::vector<double> tracts = read_table(dir + in.str("input_elemental", "input.elemental"), (size_t)E, 3);
+    ck(rdc_set_elem_field(ctx, 0, tracts.data(), 3), "rdc_set_elem_field");
+  }
+  if (model == RDC_RIPF) {
+    std::vector<double> rt = read_table(dir + in.str("input_nodal_RT", "input.nodal~RT"), (size_t)N, 2);
+    ck(rdc_set_nodal_field(ctx, 0, rt.data(), 2), "rdc_set_nodal_field");
+  }
+  ck(rdc_set_solution(ctx, u0.data()), "rdc_set_solution");
+  ck(rdc_set_subdomains(ctx, n_regions > 1 ? region.data() : nullptr, n_regions), "rdc_set_subdomains");
+  if (model == RDC_RIPF) {   // ripf.C:50-53: check_solution once before the loop, at time 0
+    ck(rdc_set_time(ctx, 0.0), "rdc_set_time");
+    ck(rdc_set_dt(ctx, dt), "rdc_set_dt");
+    ck(rdc_clamp(ctx), "rdc_clamp");
+  }
+
+  std::ofstream csv(dir + in.str("output_CSV", "output.csv"));
+  csv.precision(17);
+  auto cond1 = [&](int var, double div, double lo, double hi) {
+    rdc_range_cond c;
+    memset(&c, 0, sizeof(c));
+    c.w[var] = 1.0; c.div = div; c.lo = lo; c.hi = hi;
+    return c;
+  };
+  auto volume = [&](int ncond, const rdc_range_cond* c) {
+    std::vector<double> v((size_t)n_regions);
+    ck(rdc_region_volumes(ctx, ncond, c, v.data()), "rdc_region_volumes");
+    return v;
+  };
+  auto save_solution = [&](double time) {
+    if (model == RDC_ADPM) {   // adpm.C:690-829
+      if (time == 0.0) {
+        csv << "\"TIME\"";
+        for (int id : parcellation) csv << ",\"CONCENTRATION__A_b__" << id << "\",\"CONCENTRATION__Tau__" << id << "\"";
+        for (int id : parcellation) csv << ",\"VOLUME__A_b__" << id << "\",\"VOLUME__Tau__" << id << "\"";
+        csv << std::endl;
+      }
+      std::vector<double> cA((size_t)n_regions), cT((size_t)n_regions);
+      ck(rdc_region_last_mean(ctx, 1, cA.data()), "rdc_region_last_mean");
+      ck(rdc_region_last_mean(ctx, 2, cT.data()), "rdc_region_last_mean");
+      const rdc_range_cond a = cond1(1, 1.0, in.real("range/A_b/min", 1.0e-12), in.real("range/A_b/max", 1.0e+12));
+      const rdc_range_cond b = cond1(2, 1.0, in.real("range/Tau/min", 1.0e-12), in.real("range/Tau/max", 1.0e+12));
+      const std::vector<double> vA = volume(1, &a), vT = volume(1, &b);
+      csv << time;
+      for (int r = 0; r < n_regions; r++) csv << ',' << cA[r] << ',' << cT[r];
+      for (int r = 0; r < n_regions; r++) csv << ',' << vA[r] << ',' << vT[r];
+      csv << std::endl;
+    } else if (model == RDC_PIHNA) {   // pihna.C:842-976
+      if (time == 0.0)
+        csv << "\"TIME\",\"DEGREES_OF_FREEDOM\",\"ACTIVE_TUMOR_VOLUME\",\"NECROTIC_VOLUME\",\"VASCULARITY_VOLUME\",\"TOTAL_CELL_VOLUME\"" << std::endl;
+      rdc_range_cond act = cond1(1, 1.0, in.real("range/active_tumor/min", 1.0e-12), in.real("range/active_tumor/max", 1.0e+12));
+      act.w[2] = 1.0;   // c + h
+      const rdc_range_cond nec = cond1(0, 1.0, in.real("range/necrotic/min", 1.0e-12), in.real("range/necrotic/max", 1.0e+12));
+      const rdc_range_cond vas = cond1(3, 1.0, in.real("range/vascularity/min", 1.0e-12), in.real("range/vascularity/max", 1.0e+12));
+      rdc_range_cond tot = cond1(0, p[PIHNA_KAPPA_K], in.real("range/total_cell/min", 1.0e-12), in.real("range/total_cell/max", 1.0e+12));
+      tot.w[1] = tot.w[2] = tot.w[3] = 1.0;   // (n + c + h + v) / Kappa_k
+      csv << time << ',' << (long long)nv * N << ',' << volume(1, &act)[0] << ',' << volume(1, &nec)[0] << ',' << volume(1, &vas)[0]
+          << ',' << volume(1, &tot)[0] << std::endl;
+    } else {   // ripf.C:777-864 (no header: it is commented out in the reference)
+      const double HUmin = p[RIPF_HU_MIN], HUmax = p[RIPF_HU_MAX];
+      rdc_range_cond cc[2] = {cond1(0, 1.0, in.real("range_cc/HU/min", HUmin), in.real("range_cc/HU/max", HUmax)),
+                              cond1(1, 1.0, in.real("range_cc/min", 1.0e-9), HUGE_VAL)};
+      rdc_range_cond fb[2] = {cond1(0, 1.0, in.real("range_fb/HU/min", HUmin), in.real("range_fb/HU/max", HUmax)),
+                              cond1(2, 1.0, in.real("range_fb/min", 1.0e-9), HUGE_VAL)};
+      csv << time << ',' << volume(2, cc)[0] << ',' << volume(2, fb)[0] << std::endl;
+    }
+  };
+  save_solution(0.0);   // adpm.C:54
+
+  // ---- the time loop, adpm.C:60-84 ----------------------------------------------------------------------------------
+  double time = 0.0;
+  long its_total = 0;
+  for (int t = 1; t <= n_steps; t++) {
+    time += dt;
+    int its = 0;
+    double res = 0;
+    ck(rdc_step(ctx, time, dt, ksp, RDC_PC_JACOBI, 1e-12, 5000, 30, &its, &res), "rdc_step");
+    its_total += its;
+    printf(" ==== Step %4d out of %4d (Time=%9g) ==== its %d res %.3e\n", t, n_steps, time, its, res);
+    const bool out = out_step ? (t % out_step == 0) : (t == in.integer("output_time_points", n_steps));
+    if (out) save_solution(time);
+  }
+  if (!sol_out.empty()) {
+    std::vector<double> u((size_t)N * nv);
+    ck(rdc_get_solution(ctx, u.data()), "rdc_get_solution");
+    FILE* f = fopen(sol_out.c_str(), "wb");
+    if (!f || fwrite(u.data(), sizeof(double), u.size(), f) != u.size()) die("cannot write " + sol_out);
+    fclose(f);
+  }
+  rdc_stats st;
+  rdc_get_stats(ctx, &st);
+  printf("done: %d steps, %ld Krylov iterations, %lld kernel launches\n", n_steps, its_total, (long long)st.kernel_launches);
+  rdc_destroy(ctx);
+  return 0;
+}

@@ -1,4 +1,4 @@
-"""The stand-alone C++ driver (driver/adpm_driver.cpp) end to end: Gmsh mesh + input.dat + field files in, the
+"""The stand-alone C++ driver (driver/rdc_driver.cpp) end to end: Gmsh mesh + input.dat + field files in, the
 reference's time loop over the C ABI, save_solution CSV out -- compared with the Python mirror (same library, so the
 numbers must be identical) and with the oracle."""
 import os
@@ -27,6 +27,84 @@ def _write_gmsh(path, conn, xyz, ids):
         f.write("$EndElements\n")
 
 
+def _write_input(path, model, flat, extra):
+    """input.dat with every key of the model's table (angles back in degrees, like a user would write them)."""
+    from rdcfes_b200 import params as P
+    with open(path, "w") as f:
+        f.write("# written by tests/test_gpu_driver.py\n" + extra)
+        for (key, _), v in zip(P.TABLES[model], flat):
+            f.write(f"{key} = {float(np.degrees(v) if key in P._ANGLE_KEYS else v)!r}\n")
+
+
+@pytest.mark.parametrize("model", [cases.PIHNA, cases.RIPF])
+def test_cpp_driver_pihna_ripf(tmp_path, model):
+    """The same end-to-end check for the other two models with shipped run directories (run/PIHNA, run/RIPF133)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
+    length = 50.0 if model == cases.RIPF else 1.0
+    conn, xyz = cases.mesh(cases.TET4, 6, distort=0.2, length=length)
+    p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+    nv = cases.P.NVARS[model]
+    d = str(tmp_path)
+    _write_gmsh(os.path.join(d, "cube.msh"), conn, xyz, np.ones(conn.shape[0], dtype=int))
+    np.savetxt(os.path.join(d, "nodal.dat"), np.asarray(u0).reshape(-1, nv), fmt="%.17g")
+    extra = "input_GMSH = cube.msh\ninput_nodal = nodal.dat\noutput_CSV = out.csv\n"
+    if model == cases.RIPF:
+        np.savetxt(os.path.join(d, "rt.dat"), nf, fmt="%.17g")
+        extra += "input_nodal_RT = rt.dat\n"
+    nsteps, dt = 4, cases.DT[model]
+    U0 = np.asarray(u0).reshape(-1, nv)
+    if model == cases.PIHNA:
+        rng = {"range/active_tumor/min": 50.0, "range/necrotic/min": 1.0, "range/vascularity/max": 7000.0,
+               "range/total_cell/min": 0.03, "range/total_cell/max": 0.2}
+    else:
+        rng = {"range_cc/HU/min": -900.0, "range_cc/HU/max": -100.0, "range_cc/min": float(np.quantile(U0[:, 1], 0.5)),
+               "range_fb/min": -1.0}
+    extra += f"time_step_number = {nsteps}\ntime_step = {dt}\noutput_step = 2\n"
+    extra += "".join(f"{k} = {float(v)!r}\n" for k, v in rng.items())
+    _write_input(os.path.join(d, "input.dat"), model, p, extra)
+    sol = os.path.join(d, "u.bin")
+    out = subprocess.run([os.path.join(ROOT, "driver", "rdc_driver"), "-m", cases.NAMES[model], os.path.join(d, "input.dat"),
+                          "ksp=2", "solution_out=" + sol], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    u_drv = np.fromfile(sol)
+    rows = [ln.split(",") for ln in open(os.path.join(d, "out.csv")).read().strip().splitlines()]
+    if model == cases.PIHNA:
+        assert rows[0][1] == '"DEGREES_OF_FREEDOM"'
+        rows = rows[1:]
+    table = np.array([[float(x) for x in r] for r in rows])
+
+    gpu = cases.gpu_system(model, cases.TET4, conn, xyz, p, u0, ef, nf)
+    gpu.ksp = 2
+    BIG = float("inf")
+
+    def line(time):
+        if model == cases.PIHNA:
+            kappa = p[1]
+            v = [gpu.region_volumes([c])[0] for c in (([0, 1, 1, 0, 0], 1.0, 50.0, 1e12), ([1, 0, 0, 0, 0], 1.0, 1.0, 1e12),
+                                                      ([0, 0, 0, 1, 0], 1.0, 1e-12, 7000.0),
+                                                      ([1, 1, 1, 1, 0], kappa, 0.03, 0.2))]
+            return np.array([time, 5 * xyz.shape[0]] + v)
+        hu_min, hu_max = p[27], p[28]
+        cc = gpu.region_volumes([([1, 0, 0], 1.0, -900.0, -100.0), ([0, 1, 0], 1.0, rng["range_cc/min"], BIG)])[0]
+        fb = gpu.region_volumes([([1, 0, 0], 1.0, hu_min, hu_max), ([0, 0, 1], 1.0, -1.0, BIG)])[0]
+        return np.array([time, cc, fb])
+
+    ref = [line(0.0)]
+    orc = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf)
+    for t in range(1, nsteps + 1):
+        gpu.step(dt)
+        orc.step(dt, pc=O.PC_ILU)
+        if t % 2 == 0:
+            ref.append(line(gpu.time))
+    ref = np.array(ref)
+    assert table.shape == ref.shape
+    assert np.array_equal(table, ref), (table, ref)
+    assert np.array_equal(u_drv, gpu.get_solution())
+    assert np.linalg.norm(u_drv - orc.u) <= 1e-8 * np.linalg.norm(orc.u)
+    assert 0.0 < table[-1, -1]           # the thresholds select something
+    gpu.close()
+
+
 def test_cpp_driver_matches_python_mirror_and_oracle(tmp_path):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
     conn, xyz = cases.mesh(cases.TET4, 6, distort=0.2)
@@ -50,7 +128,7 @@ def test_cpp_driver_matches_python_mirror_and_oracle(tmp_path):
             f.write(f"{k} = {v!r}\n")
         f.write("taxis/A_b = 999.0   # ignored key, like in run/HCP102513/input.dat\n")
     sol = os.path.join(d, "u.bin")
-    out = subprocess.run([os.path.join(ROOT, "driver", "adpm_driver"), os.path.join(d, "input.dat"), "ksp=2",
+    out = subprocess.run([os.path.join(ROOT, "driver", "rdc_driver"), "-m", "adpm", os.path.join(d, "input.dat"), "ksp=2",
                           "solution_out=" + sol], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     u_drv = np.fromfile(sol)
