@@ -6,7 +6,8 @@
 
 namespace rdc {
 
-static constexpr unsigned long long P2P_TIMEOUT_NS = 4000000000ull;
+// generous: ranks may reach their first exchange seconds apart (caller-side work between rdc_create and the first step)
+static constexpr unsigned long long P2P_TIMEOUT_NS = 60000000000ull;
 static constexpr int HALO_MAX_BLK = 256;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {

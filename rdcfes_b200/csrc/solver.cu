@@ -145,9 +145,10 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NVAL], int nval, double*
       double got = 0.0;
       if (q < ar.nranks && k < nval) {
         ll_store(&ar.peer[q]->ll[par][ar.me][k][0], s_tot[k], tag);
-        const unsigned long long t0 = clock64();
+        const unsigned long long t0 = global_ns();
+        int spins = 0;
         while (!ll_load(&ar.mine->ll[par][q][k][0], tag, &got)) {
-          if (clock64() - t0 > 8000000000ll) { ar.mine->error = 1; break; }
+          if ((++spins & 1023) == 0 && global_ns() - t0 > P2P_TIMEOUT_NS) { ar.mine->error = 1; break; }
         }
       }
       __syncthreads();
