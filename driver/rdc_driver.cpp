@@ -21,12 +21,14 @@
 #include <algorithm>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <set>
 #include <sstream>
 #include <string>
 #include <vector>
 
 #include "param_tables.h"
+#include "vtu_writer.h"
 #include "rdc.h"
 
 static void die(const std::string& msg) {
@@ -256,7 +258,24 @@ int main(int argc, char** argv) {
       csv << time << ',' << volume(2, cc)[0] << ',' << volume(2, fb)[0] << std::endl;
     }
   };
+  // ParaView output (paraview.update_pvd, adpm.C:55,82): only when input.dat names output_PARAVIEW
+  static const char* kVarNames[3][5] = {{"PrP", "A_b", "Tau", "", ""}, {"n", "c", "h", "v", "a"}, {"HU", "cc", "fb", "", ""}};
+  std::vector<std::string> var_names;
+  for (int a = 0; a < nv; a++) var_names.push_back(kVarNames[model == RDC_ADPM ? 0 : model == RDC_PIHNA ? 1 : 2][a]);
+  const VtuMesh vmesh = {mesh.nen, &mesh.xyz, &mesh.conn, &mesh.subdomain, nullptr};
+  std::unique_ptr<PvdCollection> pvd;
+  if (in.kv.count("output_PARAVIEW")) {
+    pvd.reset(new PvdCollection(dir + in.str("output_PARAVIEW", "output4paraview")));
+    if (!pvd->ok()) die("cannot open the .pvd collection");
+  }
+  std::vector<double> u_host((size_t)N * nv);
+  auto update_pvd = [&](unsigned t) {
+    if (!pvd) return;
+    ck(rdc_get_solution(ctx, u_host.data()), "rdc_get_solution");   // the only device->host copy of the solution
+    if (!pvd->add(vmesh, var_names, u_host, t)) die("cannot write the .vtu file");
+  };
   save_solution(0.0);   // adpm.C:54
+  update_pvd(0);        // adpm.C:55
 
   // ---- the time loop, adpm.C:60-84 ----------------------------------------------------------------------------------
   double time = 0.0;
@@ -269,7 +288,7 @@ int main(int argc, char** argv) {
     its_total += its;
     printf(" ==== Step %4d out of %4d (Time=%9g) ==== its %d res %.3e\n", t, n_steps, time, its, res);
     const bool out = out_step ? (t % out_step == 0) : (t == in.integer("output_time_points", n_steps));
-    if (out) save_solution(time);
+    if (out) { save_solution(time); update_pvd((unsigned)t); }
   }
   if (!sol_out.empty()) {
     std::vector<double> u((size_t)N * nv);

@@ -113,3 +113,38 @@ def test_oracle_on_the_shipped_meshes(name, etype):
         got = _pins(pr, cases.DT[model], O)
         ref = d["pin_" + cases.NAMES[model]]
         assert np.allclose(got, ref, rtol=1e-10, atol=0), (cases.NAMES[model], got, ref)
+
+
+def test_vtu_writer_of_the_cpp_driver(tmp_path):
+    """driver/vtu_writer.h needs no GPU: a tiny program writes a two-tet mesh; the XML is read back and compared with
+    the layout of the reference's Paraview_IO (paraview.h:60-150, 158-198)."""
+    import xml.etree.ElementTree as ET
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include "vtu_writer.h"
+int main(int argc, char** argv) {
+  std::vector<double> xyz = {0,0,0, 1,0,0, 0,1,0, 0,0,1, 1,1,1};
+  std::vector<int32_t> conn = {0,1,2,3, 1,2,3,4};
+  std::vector<int> sub = {7, 3};
+  VtuMesh m = {4, &xyz, &conn, &sub, nullptr};
+  std::vector<double> u = {1,10, 2,20, 3,30, 4,1e-320, 5,50};
+  PvdCollection pvd(argv[1]);
+  return pvd.add(m, {"A", "B"}, u, 0) && pvd.add(m, {"A", "B"}, u, 20) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(os.path.dirname(HERE), "driver"), "-o", str(exe), str(src)])
+    base = str(tmp_path / "out")
+    subprocess.check_call([str(exe), base])
+    pvd = ET.parse(base + ".pvd").getroot()
+    sets = pvd.find("Collection").findall("DataSet")
+    assert [s.get("timestep") for s in sets] == ["0", "20"] and sets[1].get("file") == "out-20.vtu"
+    piece = ET.parse(base + "-20.vtu").getroot().find("UnstructuredGrid").find("Piece")
+    assert piece.get("NumberOfPoints") == "5" and piece.get("NumberOfCells") == "2"
+    arr = {a.get("Name"): np.array(a.text.split(), dtype=float) for a in piece.iter("DataArray")}
+    assert np.array_equal(arr["position"], [0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 1, 1])
+    assert np.array_equal(arr["node_ID"], [1, 2, 3, 4, 5]) and np.array_equal(arr["element_ID"], [1, 2])
+    assert np.array_equal(arr["A"], [1, 2, 3, 4, 5]) and np.array_equal(arr["B"], [10, 20, 30, 0, 50])   # denormal -> 0
+    assert np.array_equal(arr["region_ID"], [7, 3]) and np.array_equal(arr["processor_ID"], [0, 0])
+    assert np.array_equal(arr["connectivity"], [0, 1, 2, 3, 1, 2, 3, 4])
+    assert np.array_equal(arr["offsets"], [4, 8]) and np.array_equal(arr["types"], [10, 10])

@@ -121,7 +121,7 @@ def test_cpp_driver_matches_python_mirror_and_oracle(tmp_path):
     lo, hi = 0.02, 0.5
     with open(os.path.join(d, "input.dat"), "w") as f:
         f.write("# written by tests/test_gpu_driver.py\ninput_GMSH = 'cube.msh'\ninput_nodal = 'nodal.dat'\n"
-                "input_elemental = 'elemental.dat'\noutput_CSV = out.csv\n")
+                "input_elemental = 'elemental.dat'\noutput_CSV = out.csv\noutput_PARAVIEW = 'view'\n")
         f.write(f"time_step_number = {nsteps}\ntime_step = {dt}\noutput_step = 2\n")
         f.write(f"range/A_b/min = {lo}\nrange/A_b/max = {hi}\nrange/Tau/min = {lo}\nrange/Tau/max = {hi}\n")
         for k, v in kv.items():
@@ -158,6 +158,15 @@ def test_cpp_driver_matches_python_mirror_and_oracle(tmp_path):
     ref = np.array(ref)
     assert np.array_equal(table, ref), np.abs(table - ref).max()
     assert np.array_equal(u_drv, gpu.get_solution())
+    # ParaView collection: steps 0, 2, 4; the point data of the last file is the final solution
+    import xml.etree.ElementTree as ET
+    sets = ET.parse(os.path.join(d, "view.pvd")).getroot().find("Collection").findall("DataSet")
+    assert [x.get("timestep") for x in sets] == ["0", "2", "4"]
+    piece = ET.parse(os.path.join(d, "view-4.vtu")).getroot().find("UnstructuredGrid").find("Piece")
+    arr = {a.get("Name"): np.array(a.text.split(), dtype=float) for a in piece.iter("DataArray")}
+    for j, name in enumerate(("PrP", "A_b", "Tau")):
+        assert np.array_equal(arr[name], u_drv[j::3])
+    assert np.array_equal(arr["region_ID"], gmsh_ids) and np.array_equal(arr["connectivity"], conn.ravel())
     # and the oracle: solution to 1e-8, CSV quantities from the oracle's serial loops on ITS solution to 1e-6
     assert np.linalg.norm(u_drv - orc.u) <= 1e-8 * np.linalg.norm(orc.u)
     cA = O.region_last_mean(cases.TET4, conn, xyz, orc.u, 1, region, 3)
