@@ -9,14 +9,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_distributed_matches_oracle(world):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(here, "dist_worker.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(29541 + world), os.path.join(here, "dist_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     print(res.stdout[-3000:])
     print(res.stderr[-3000:])
