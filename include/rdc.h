@@ -21,6 +21,11 @@
  *                                  proteas.C:707-750, coupled_hcc.C:695-731)
  *   rdc_step                    <- one iteration of the time loop body (adpm.C:63-76)
  *   rdc_get_solution            <- es.build_solution_vector (paraview.h:24-25) at output steps
+ *   rdc_get_solution_owned      <- the rank-local part of system.solution (distributed PETSc vector)
+ *   rdc_set_subdomains /
+ *   rdc_region_volumes /
+ *   rdc_region_last_mean        <- the element loops of save_solution (adpm.C:690-829, pihna.C:842-976,
+ *                                  ripf.C:777-864) behind the per-case CSV output
  *   rdc_download_csr            <- parity only: the assembled PETSc AIJ matrix and rhs
  *
  * Rules: plain C types only; every function returns 0 (RDC_OK) or a negative RDC_E* code; the message
@@ -45,7 +50,7 @@ typedef struct rdc_ctx rdc_ctx;
 enum rdc_model { RDC_ADPM = 0, RDC_PIHNA = 1, RDC_RIPF = 2, RDC_PROTEAS = 3, RDC_HCC = 4 };
 enum rdc_elem  { RDC_TET4 = 4, RDC_HEX8 = 8 };
 enum rdc_ksp   { RDC_KSP_GMRES = 0, RDC_KSP_CG = 1, RDC_KSP_BICGSTAB = 2 };
-enum rdc_pc    { RDC_PC_JACOBI = 0, RDC_PC_NONE = 1, RDC_PC_BJACOBI = 2 /* v x v nodal block */ };
+enum rdc_pc    { RDC_PC_JACOBI = 0, RDC_PC_NONE = 1, RDC_PC_BJACOBI = 2 /* reserved (v x v nodal block): RDC_E_ARG today */ };
 
 enum rdc_status {
   RDC_OK = 0,
@@ -193,8 +198,11 @@ int rdc_set_dt(rdc_ctx*, double dt);            /* es.parameters "time_step"; ne
 /* ---- the hot path ----------------------------------------------------------------------------- */
 int rdc_rotate(rdc_ctx*);                                   /* older <- old <- current */
 int rdc_assemble(rdc_ctx*, double time, double dt);         /* K, F from old solution; device resident */
+/* KSPSolve: initial guess = current solution; converged when ||B r|| <= max(rtol ||B b||, 1e-50) (PETSc default test,
+ * left preconditioning).  `restart` is used by GMRES only (<= 0: 30).  A BiCGStab breakdown (rho or omega = 0)
+ * continues with GMRES from the current iterate; RDC_E_DIVERGED is returned only for a NaN residual. */
 int rdc_solve(rdc_ctx*, int ksp, int pc, double rtol, int maxits, int restart,
-              int* iterations, double* resnorm);            /* initial guess = current solution */
+              int* iterations, double* resnorm);
 int rdc_clamp(rdc_ctx*);                                    /* the model's check_solution, at ctx time */
 /* time += dt is the caller's business (adpm.C:63): pass the NEW time. rotate+assemble+solve+clamp. */
 int rdc_step(rdc_ctx*, double time, double dt, int ksp, int pc, double rtol, int maxits, int restart,
