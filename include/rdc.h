@@ -250,6 +250,9 @@ struct rdc_stats {
   int64_t bytes_index;      /* index overhead read per assembly (maps), reported separately */
   int64_t kernel_launches;  /* kernels launched by this context so far                 */
   int     ripf_rt_total_max;/* RIPF: int(max RT_total) (ripf.C:772)                    */
+  /* running totals since rdc_create (phase times are resolved lazily, without host synchronisation inside a step) */
+  double sum_ms_assemble, sum_ms_solve, sum_ms_clamp, sum_ms_spmv;
+  int64_t sum_iterations, sum_n_spmv, n_solves;
 };
 int rdc_get_stats(rdc_ctx*, struct rdc_stats*);
 /* Host-only probe of the node partition and halo lists of rank `rank` (no device needed; used by the CPU

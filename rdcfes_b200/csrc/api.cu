@@ -442,12 +442,28 @@ extern "C" int rdc_rotate(rdc_ctx* c) {
   return RDC_OK;
 }
 
+// Elapsed times of the phases are read from their event pairs lazily: non-blocking at the start of the next phase of
+// the same kind (the events of the previous step completed long ago), blocking only in rdc_get_stats.
+static void resolve_timings(rdc_ctx* c, bool wait) {
+  auto one = [&](bool& pending, cudaEvent_t* ev, double& last, double& sum) {
+    if (!pending) return;
+    if (wait ? cudaEventSynchronize(ev[1]) != cudaSuccess : cudaEventQuery(ev[1]) != cudaSuccess) { cudaGetLastError(); return; }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) { last = ms; sum += ms; }
+    pending = false;
+  };
+  one(c->t_asm_pending, c->ev_asm, c->st.ms_assemble, c->st.sum_ms_assemble);
+  one(c->t_sol_pending, c->ev_sol, c->st.ms_solve, c->st.sum_ms_solve);
+  one(c->t_clamp_pending, c->ev_clamp, c->st.ms_clamp, c->st.sum_ms_clamp);
+}
+
 extern "C" int rdc_assemble(rdc_ctx* c, double time, double dt) {
   CHECK_CTX(c);
   if (!c->have_params) { c->err = "rdc_assemble: rdc_set_params has not been called"; return RDC_E_STATE; }
   if (!(dt > 0.0)) { c->err = "rdc_assemble: dt must be positive"; return RDC_E_ARG; }
   c->time = time; c->dt = dt;
   // no host synchronisation here: the elapsed time is read when the statistics are asked for
+  resolve_timings(c, false);
   cudaEventRecord(c->ev_asm[0], c->stream);
   int rc = launch_assemble(c);
   if (rc) return rc;
@@ -463,11 +479,16 @@ extern "C" int rdc_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, i
   int its = 0;
   double res = 0;
   c->st.n_spmv = 0;
+  resolve_timings(c, false);
   cudaEventRecord(c->ev_sol[0], c->stream);
   int rc = solver_solve(c, ksp, pc, rtol, maxits, restart, &its, &res);
   cudaEventRecord(c->ev_sol[1], c->stream);
   c->t_sol_pending = true;
   c->st.iterations = its;
+  c->st.sum_iterations += its;
+  c->st.sum_n_spmv += c->st.n_spmv;
+  c->st.sum_ms_spmv += c->st.ms_spmv_total;
+  c->st.n_solves++;
   c->st.resnorm = res;
   if (iterations) *iterations = its;
   if (resnorm) *resnorm = res;
@@ -480,6 +501,7 @@ extern "C" int rdc_clamp(rdc_ctx* c) {
     if (!c->have_params || !c->d_rt) { c->err = "rdc_clamp (RIPF): parameters and RT dose field are required"; return RDC_E_STATE; }
     if (!(c->dt > 0.0)) { c->err = "rdc_clamp (RIPF): time step unknown; call rdc_assemble/rdc_step or rdc_set_dt first"; return RDC_E_STATE; }
   }
+  resolve_timings(c, false);
   cudaEventRecord(c->ev_clamp[0], c->stream);
   int rc = launch_clamp(c);
   if (rc) return rc;
@@ -576,16 +598,7 @@ extern "C" int rdc_bench_stream(rdc_ctx* c, int reps, int ctas_per_sm, double* m
 extern "C" int rdc_get_stats(rdc_ctx* c, struct rdc_stats* s) {
   if (!c || !s) return RDC_E_ARG;
   cudaSetDevice(c->device);
-  auto resolve = [&](bool& pending, cudaEvent_t* ev, double& out) {
-    if (!pending) return;
-    float ms = 0;
-    if (cudaEventSynchronize(ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) out = ms;
-    pending = false;
-  };
-  resolve(c->t_asm_pending, c->ev_asm, c->st.ms_assemble);
-  resolve(c->t_sol_pending, c->ev_sol, c->st.ms_solve);
-  resolve(c->t_clamp_pending, c->ev_clamp, c->st.ms_clamp);
-  solver_spmv_time(c);
+  resolve_timings(c, true);
   *s = c->st;
   return RDC_OK;
 }

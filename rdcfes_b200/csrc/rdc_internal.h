@@ -176,7 +176,6 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
 int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done = false);
 int launch_clamp(rdc_ctx* c);
 int launch_stream_probe(rdc_ctx* c, int ctas_per_sm);
-void solver_spmv_time(rdc_ctx* c);   // resolves the lazily summed SpMV event times into st.ms_spmv_total
 int spmv_masks_ok();                // solver.cu's entry masks agree with the model definitions
 int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc);     // dst_loc[l] = src[dofmap[l]]
 int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob);    // owned part only

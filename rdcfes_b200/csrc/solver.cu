@@ -52,7 +52,6 @@ struct SolverWork {
   static constexpr int MAX_EV = 512;
   cudaEvent_t ev[2 * MAX_EV];
   int n_ev_used = 0;
-  bool spmv_time_pending = false;
   static constexpr int RING = 8;
   int* h_ring = nullptr;     // pinned copies of the convergence flag
   int4* tiles = nullptr;     // SpMV tiles {row0, nrows, first block, nblocks} (k_spmv_tma)
@@ -1435,10 +1434,18 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
     }
   }
   else { c->err = "unknown ksp"; return RDC_E_ARG; }
-  // The event-bracketed SpMV launches of this solve are summed lazily (solver_spmv_time) so that the solve
-  // does not end with a host synchronisation.  Launches issued after convergence return at once (device-side
-  // flag) and add ~0, so the mean over the REAL SpMVs is total / (its * spmv per its).
-  W->spmv_time_pending = true;
+  // Every solver ends with a stream synchronisation (the final poll), so the event pairs around the SpMV launches of
+  // this solve are complete: sum them now.  Launches issued after convergence return at once (device-side flag) and
+  // add ~0, so the mean over the REAL SpMVs is total / (its * spmv per its).
+  {
+    double tot = 0.0;
+    for (int k = 0; k < W->n_ev_used; k++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, W->ev[2 * k], W->ev[2 * k + 1]) == cudaSuccess) tot += ms;
+      else cudaGetLastError();
+    }
+    c->st.ms_spmv_total = tot;
+  }
   c->st.n_spmv = (*its) * (ksp == RDC_KSP_BICGSTAB ? 2 : 1);
   return rc;
 }
@@ -1463,19 +1470,6 @@ int launch_stream_probe(rdc_ctx* c, int ctas_per_sm) {
   c->st.kernel_launches++;
   RDC_CUDA(cudaGetLastError());
   return 0;
-}
-
-void solver_spmv_time(rdc_ctx* c) {
-  SolverWork* W = c->work;
-  if (!W || !W->spmv_time_pending) return;
-  cudaStreamSynchronize(c->stream);
-  double tot = 0.0;
-  for (int k = 0; k < W->n_ev_used; k++) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, W->ev[2 * k], W->ev[2 * k + 1]) == cudaSuccess) tot += ms;
-  }
-  c->st.ms_spmv_total = tot;
-  W->spmv_time_pending = false;
 }
 
 }  // namespace rdc

@@ -26,7 +26,10 @@ class Stats(C.Structure):
                 ("resnorm", C.c_double), ("resnorm0", C.c_double),
                 ("n_nodes_local", C.c_int64), ("n_nodes_ghost", C.c_int64), ("n_elems_local", C.c_int64),
                 ("nnzb_local", C.c_int64), ("bytes_assemble", C.c_int64), ("bytes_spmv", C.c_int64),
-                ("bytes_index", C.c_int64), ("kernel_launches", C.c_int64), ("ripf_rt_total_max", C.c_int)]
+                ("bytes_index", C.c_int64), ("kernel_launches", C.c_int64), ("ripf_rt_total_max", C.c_int),
+                ("sum_ms_assemble", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_clamp", C.c_double),
+                ("sum_ms_spmv", C.c_double), ("sum_iterations", C.c_int64), ("sum_n_spmv", C.c_int64),
+                ("n_solves", C.c_int64)]
 
 
 EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_distributed", "rdc_comm_unique_id",
