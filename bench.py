@@ -283,9 +283,10 @@ def main():
         "roofline": {"kernel": ("k_spmv_tma<3,KMASK_ADPM,*,2>" if args.model == "adpm" else "k_spmv_tma<5,KMASK_PIHNA,*,2>") + " (row-local block-CSR SpMV, TMA-staged, fused Jacobi scaling "
                                "and BiCGStab dot products)", "bound": "hbm",
                      "achieved": spmv_gbs, "peak": peak, "unit": "GB/s", "frac": spmv_gbs / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-                     # workload on one GPU (profiles/r1d_spmv_tma_full.csv); other sizes were not captured
-                     "traffic": 1.673e9 if (args.n == 119 and world == 1 and args.model == "adpm") else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full captures of this
+                     # workload on one GPU (profiles/r1h_assemble_spmv_full.csv: 1.672 + 0.043 GB; r1d: 1.630 + 0.043 GB);
+                     # other sizes were not captured
+                     "traffic": 1.716e9 if (args.n == 119 and world == 1 and args.model == "adpm") else None,
                      "peak_source": peak_src, "bytes_per_launch": int(st.bytes_spmv), "ms_per_launch": spmv_ms,
                      "launches_timed": acc["n_spmv"], "frac_of_nominal_8TBs": spmv_gbs / 8000.0},
         "roofline_assembly": {"kernel": ("k_assemble<Adpm,4,128,4>" if args.model == "adpm" else "k_assemble<Pihna,4,128,2>") + " (fp64-pipe bound, see DESIGN.md 4.1)", "bound": "hbm", "achieved": asm_gbs, "peak": peak,
