@@ -322,19 +322,29 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
     // node owned by that rank.  Derived from the replicated mesh, so no communication is needed.
     std::vector<std::vector<int32_t>> send((size_t)nranks);
     {
-      std::vector<int32_t> mark((size_t)N * 1, -1);  // last rank a node was queued for (per pass)
-      for (int q = 0; q < nranks; q++) {
-        if (q == rank) continue;
-        for (int64_t e = 0; e < E; e++) {
-          bool has_q = false, has_me = false;
-          for (int i = 0; i < nen; i++) { const int o = owner[conn[e * nen + i]]; has_q |= (o == q); has_me |= (o == rank); }
-          if (!has_q || !has_me) continue;
-          for (int i = 0; i < nen; i++) {
-            const int32_t g = conn[e * nen + i];
-            if (owner[g] == rank && mark[g] != q) { mark[g] = q; send[q].push_back(g); }
+      // one pass over the LOCAL elements (every element with a node of mine is local): an owned node goes to every
+      // other rank that owns a node of the same element; duplicates are removed by the sort below
+      int owners[RDC_MAX_NEN];
+      for (int64_t le = 0; le < S.E_loc; le++) {
+        const int64_t e = S.elem_glob[le];
+        bool mixed = false;
+        for (int i = 0; i < nen; i++) { owners[i] = owner[conn[e * nen + i]]; mixed |= owners[i] != rank; }
+        if (!mixed) continue;
+        for (int i = 0; i < nen; i++) {
+          if (owners[i] != rank) continue;
+          const int32_t g = conn[e * nen + i];
+          for (int j = 0; j < nen; j++) {
+            const int q = owners[j];
+            if (q == rank) continue;
+            bool seen = false;
+            for (int k = 0; k < j; k++) seen |= owners[k] == q;
+            if (!seen) send[q].push_back(g);
           }
         }
-        std::sort(send[q].begin(), send[q].end());  // the receiver orders its ghosts by global id too
+      }
+      for (int q = 0; q < nranks; q++) {   // the receiver orders its ghosts by global id too
+        std::sort(send[q].begin(), send[q].end());
+        send[q].erase(std::unique(send[q].begin(), send[q].end()), send[q].end());
       }
     }
     for (int q = 0; q < nranks; q++) {
