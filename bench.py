@@ -14,7 +14,8 @@ Krylov solve (BiCGStab + Jacobi by default, --ksp 0 = libMesh's GMRES(30)) to rt
   * roofline : the dominant kernel (block-CSR SpMV): algorithmic bytes / mean launch time, timed live with an
             event pair around every SpMV launch of the timed steps; assembly reported next to it
   * cpu_baseline : the CPU oracle (port of the reference path: element loop + scalar CSR + GMRES(30) +
-            block-Jacobi/ILU(0)) on the box's host cores, on a bounded sample mesh, scaled per element
+            block-Jacobi/ILU(0)) on the box's host cores: a few steps of the SAME mesh (about 10 s per step on 16
+            cores); --cpu-n picks a smaller sample mesh, then scaled per element
 N > 1 (torchrun): strong scaling of the same mesh, METIS node partition, ghost exchange + all-reduce over NVLink
 peer memory inside the Krylov kernels (NCCL for set-up and as fallback).  --model pihna: secondary 5-species case.
 --impl reference: times the CPU port only (the real rdcFEs binary needs libMesh/PETSc/MPI: not installable).
@@ -132,7 +133,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"S1 ADPM P-full, unit-cube Kuhn tets n={args.n} ({E_full} tets), dt={DT}"},
+           "config": {"workload": f"S1 ADPM P-full, unit-cube Kuhn tets n={args.n} ({E_full} tets, {(args.n + 1) ** 3} nodes, "
+                                  f"{3 * (args.n + 1) ** 3} dofs), dt={DT}, GMRES(30)+BJacobi/ILU(0) rtol 1e-12 (libMesh defaults)",
+                      "parallelism": f"CPU port of the reference path, {ncores} OpenMP threads (one ILU(0) block per thread)"},
            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": ncores, "kind": "port",
                             "sample": f"n={n_sample} ({E} tets) timed {sec:.3f} s/step ({ta:.3f} assemble + {ts:.3f} solve, "
                                       f"{its:.0f} GMRES(30)+BJacobi/ILU0 its), scaled x{E_full / E:.1f} by element count"},
@@ -148,7 +151,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--n", "--cells", dest="n", type=int, default=119,
                     help="cells per edge (119 -> 10.1 M tets; under torchrun spell it --cells: --n is ambiguous there)")
-    ap.add_argument("--cpu-n", type=int, default=90, help="sample mesh of the CPU baseline (90 -> 4.4 M tets)")
+    ap.add_argument("--cpu-n", type=int, default=119,
+                    help="mesh of the CPU baseline: by default the workload itself (a few steps of it are the bounded sample)")
     ap.add_argument("--ksp", type=int, default=2, help="0 GMRES(30) (libMesh default), 1 CG, 2 BiCGStab; all Jacobi, rtol 1e-12")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partitioner", type=int, default=0)
