@@ -172,11 +172,15 @@ int region_setup(rdc_ctx* c, const int32_t* region, int n_regions) {
   if (region)
     for (int64_t e = 0; e < S.E_glob; e++)
       if (region[e] < 0 || region[e] >= n_regions) { c->err = "rdc_set_subdomains: region id out of range"; return RDC_E_ARG; }
-  // first node of every local element decides who counts it
+  // first node of every local element decides who counts it (the host copy of the connectivity was released after
+  // rdc_create: read it back once -- set-up time, one plain copy)
   std::vector<int32_t> first((size_t)S.E_loc);
-  RDC_CUDA(cudaMemcpy2DAsync(first.data(), sizeof(int32_t), c->d_conn, sizeof(int32_t) * c->nen, sizeof(int32_t), (size_t)S.E_loc,
-                             cudaMemcpyDeviceToHost, c->stream));
-  RDC_CUDA(cudaStreamSynchronize(c->stream));
+  {
+    std::vector<int32_t> hconn((size_t)S.E_loc * c->nen);
+    RDC_CUDA(cudaMemcpyAsync(hconn.data(), c->d_conn, hconn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    RDC_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t le = 0; le < S.E_loc; le++) first[le] = hconn[(size_t)le * c->nen];
+  }
   RegionWork* R = new RegionWork();
   c->region = R;
   R->n_regions = n_regions;
