@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  The product package (rdcfes_b200/) never imports this module.
-Parity status: "parity unpinned" upstream (the reference has no tests); pinned by tests/test_oracle_kat.py.
+Parity status: pinned to the reference's own compiled sources (oracle/ref.py, tests/test_ref_pin.py) and by the
+known-answer tests of tests/test_oracle_kat.py; see the header of rdc_oracle.c.
 """
 from __future__ import annotations
 

@@ -4,11 +4,15 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as the
  * checker and as the reported CPU baseline.
  *
- * PARITY STATUS: "parity unpinned" upstream -- the reference ships no tests, golden vectors or expected
- * outputs and its libMesh/PETSc dependencies are not installable here, so the
- * reference binary cannot be run.  The restatement is pinned instead by independent known-answer tests
- * (tests/test_oracle_kat.py: analytic P1/Q1 element matrices, quadrature exactness, constant
- * preservation, row sums, finite-difference Jacobian checks, sparse direct solve).
+ * PARITY STATUS: pinned to the reference's own sources for everything that is in-tree.  oracle/ref.py compiles
+ * /root/reference/src/{adpm,pihna,ripf,proteas,coupled_hcc}.C UNCHANGED (g++, serial libMesh stand-in
+ * oracle/ref_shim/) into oracle/_ref/; tests/test_ref_pin.py runs this restatement next to them (K, F, check_solution,
+ * the RIPF state machine, save_solution, input()) and against the vectors they produced (tests/golden/ref_*.npz):
+ * F and the clamped states agree bit for bit, K entries to <= 1e-12 pure relative.  What stays "unpinned upstream" is
+ * only what is not under /root/reference: libMesh's FE tables / FEMap / dof numbering and PETSc's KSP (the reference
+ * ships no tests or expected outputs); those are restated identically in the oracle and in
+ * the stand-in and checked by independent known-answer tests (tests/test_oracle_kat.py: analytic P1/Q1 element
+ * matrices, quadrature exactness, constant preservation, row sums, finite-difference Jacobians, sparse direct solve).
  *
  * What is restated (reference file:line):
  *   rate laws            utils.h:69-90,100-187
