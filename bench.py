@@ -105,8 +105,10 @@ def workload(n, model="adpm"):
     return conn, xyz, synth.adpm_params("full"), u0, tracts
 
 
-def cpu_port_run(n, steps, warmup, nthreads):
-    """The CPU port on a bounded sample mesh: returns (seconds per step, elements, its per step, phases)."""
+def cpu_port_run(n, steps, warmup, nthreads, keep_state=None):
+    """The CPU port on a bounded sample mesh: returns (seconds per step, elements, its per step, phases).
+    keep_state (a dict) receives the oracle's solution after the warmup + steps steps from u0: the parity check
+    of the bench line compares the GPU path with it on the SAME mesh."""
     from oracle import oracle as O
     conn, xyz, params, u0, tracts = workload(n)
     pr = O.Problem(O.ADPM, O.TET4, conn, xyz, params, u0, elem_field=tracts, nthreads=nthreads)
@@ -117,6 +119,9 @@ def cpu_port_run(n, steps, warmup, nthreads):
         t1 = time.perf_counter()
         if k >= warmup:
             times.append(t1 - t0); its_all.append(its); ta.append(pr.t_assemble); ts.append(pr.t_solve)
+    if keep_state is not None:
+        keep_state["u"] = pr.u.copy()
+        keep_state["steps"] = warmup + steps
     return float(np.mean(times)), conn.shape[0], float(np.mean(its_all)), float(np.mean(ta)), float(np.mean(ts))
 
 
@@ -226,6 +231,11 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop(mark0, sampler.mark()) if rank == 0 else None
+    # untimed: the state after warm-up + timed steps from u0 is the same problem at every N -- its norm and sum let the
+    # 1/2/4/8-GPU lines of a scaling run be compared with each other (they must agree to the solver tolerance)
+    u_end = sysm.get_solution()
+    solution_check = {"l2": float(np.linalg.norm(u_end)), "sum": float(u_end.sum()), "steps_from_u0": args.warmup + args.steps,
+                      "min": float(u_end.min())}
     st1 = sysm.stats()
     launches = st1.kernel_launches - launches0
     acc = {"its": st1.sum_iterations - st0.sum_iterations, "ms_asm": st1.sum_ms_assemble - st0.sum_ms_assemble,
@@ -299,13 +309,35 @@ def main():
         "phases_ms_per_step": {"assemble": asm_ms, "solve": acc["ms_solve"] / args.steps,
                                "clamp": acc["ms_clamp"] / args.steps, "spmv_in_solve": acc["ms_spmv"] / args.steps},
         "krylov_its_per_step": acc["its"] / args.steps,
+        "solution_check": solution_check,
     }
+    # parity on the bench mesh itself (N = 1, untimed): the same k steps from u0 on the GPU and with the CPU oracle
+    cpu_steps, cpu_warm = 2, 1
+    want_cpu = not args.no_cpu_baseline and args.model == "adpm" and world == 1
+    u_gpu_k = None
+    if want_cpu and args.cpu_n == args.n:
+        u_np[:] = u0.ravel()
+        sysm.set_solution(u_np)
+        sysm.time = 0.0
+        for _ in range(cpu_steps + cpu_warm):
+            sysm.step(dt)
+        u_gpu_k = sysm.get_solution().copy()
     sysm.close()
     if world > 1:
         dist.destroy_process_group()
-    if not args.no_cpu_baseline and args.model == "adpm" and world == 1:  # reported at N = 1 only
+    if want_cpu:  # reported at N = 1 only
         ncores = os.cpu_count() or 1
-        sec, Es, its, ta, ts = cpu_port_run(args.cpu_n, 2, 1, ncores)
+        state = {}
+        sec, Es, its, ta, ts = cpu_port_run(args.cpu_n, cpu_steps, cpu_warm, ncores, keep_state=state)
+        if u_gpu_k is not None:
+            uo, ug = state["u"].reshape(-1, nv), u_gpu_k.reshape(-1, nv)
+            out["parity"] = {"against": "CPU oracle (oracle/rdc_oracle.c, pinned to the reference's own sources by "
+                                        "tests/test_ref_pin.py), same mesh, same u0, GMRES(30)+BJacobi/ILU(0) vs the GPU solver",
+                             "steps": state["steps"],
+                             "rel_l2": float(np.linalg.norm(ug - uo) / np.linalg.norm(uo)),
+                             "per_species_rel_l2": [float(np.linalg.norm(ug[:, a] - uo[:, a]) / max(np.linalg.norm(uo[:, a]), 1e-300))
+                                                    for a in range(nv)],
+                             "max_abs": float(np.abs(ug - uo).max()), "tolerance": 1e-6}
         val = 1.0 / (sec * E / Es)
         out["cpu_baseline"] = {"value": val, "unit": "steps/s", "cores": ncores, "kind": "port",
                                "sample": f"n={args.cpu_n} ({Es} tets) {sec:.3f} s/step ({ta:.3f} assemble + {ts:.3f} solve, "

@@ -234,6 +234,9 @@ int rdc_bench_stream(rdc_ctx*, int reps, int ctas_per_sm, double* mean_ms, int64
 int rdc_download_csr(rdc_ctx*, int64_t* n_rows, int64_t* nnz,
                      int64_t** rows, int64_t** rowptr, int32_t** col, double** val, double** rhs);
 void rdc_free(void*);
+/* the assembled load vector F in global dof numbering (length rdc_n_dofs; distributed: every rank receives all of it):
+ * system.rhs after the assemble callback -- lets a caller form the true residual F - K u with rdc_spmv */
+int rdc_get_rhs(rdc_ctx*, double* rhs);
 
 struct rdc_stats {
   double ms_assemble;       /* last rdc_assemble, CUDA events on the context stream   */
@@ -253,6 +256,9 @@ struct rdc_stats {
   /* running totals since rdc_create (phase times are resolved lazily, without host synchronisation inside a step) */
   double sum_ms_assemble, sum_ms_solve, sum_ms_clamp, sum_ms_spmv;
   int64_t sum_iterations, sum_n_spmv, n_solves;
+  /* distributed runs: 1 when ghost values and dot products travel over NVLink peer memory (cudaIpc arenas), 0 on the
+   * NCCL transport; p2p_fused = the exchanges are finished inside the producing Krylov kernels */
+  int     p2p_on, p2p_fused;
 };
 int rdc_get_stats(rdc_ctx*, struct rdc_stats*);
 /* Host-only probe of the node partition and halo lists of rank `rank` (no device needed; used by the CPU

@@ -379,7 +379,7 @@ static int to_host(rdc_ctx* c, const double* d_loc, double* host) {
   if (c->S.nranks > 1 && (rc = allreduce_sum(c, c->d_stage, (int)c->D_glob))) return rc;
   RDC_CUDA(cudaMemcpyAsync(host, c->d_stage, (size_t)c->D_glob * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return p2p_check_error(c);
 }
 
 extern "C" int rdc_set_solution(rdc_ctx* c, const double* u) {
@@ -425,6 +425,14 @@ extern "C" int rdc_get_solution_owned(rdc_ctx* c, double* u) {
     for (int a2 = 0; a2 < c->nv; a2++) u[base + a2] = tmp[(size_t)l * c->nv + a2];
   }
   return RDC_OK;
+}
+
+extern "C" int rdc_get_rhs(rdc_ctx* c, double* rhs) {
+  CHECK_CTX(c);
+  if (!rhs) return RDC_E_ARG;
+  if (!c->assembled) { c->err = "rdc_get_rhs: nothing assembled"; return RDC_E_STATE; }
+  // d_rhs holds the owned rows only; to_host reads the owned part of a local vector
+  return to_host(c, c->d_rhs, rhs);
 }
 
 extern "C" int rdc_get_old_solution(rdc_ctx* c, double* u) {
@@ -599,6 +607,8 @@ extern "C" int rdc_get_stats(rdc_ctx* c, struct rdc_stats* s) {
   if (!c || !s) return RDC_E_ARG;
   cudaSetDevice(c->device);
   resolve_timings(c, true);
+  c->st.p2p_on = p2p_on(c) ? 1 : 0;
+  c->st.p2p_fused = (p2p_on(c) && c->opt.p2p_fused_ar && c->opt.p2p_fused_halo) ? 1 : 0;
   *s = c->st;
   return RDC_OK;
 }

@@ -115,9 +115,15 @@ static double* p2p_alloc_raw(P2P* P) {
 // ---- peer-memory set-up ------------------------------------------------------------------------------------
 // Collective over the NCCL communicator: agrees on the arena geometry (slot = the largest local vector of any
 // rank), exchanges the cudaIpc handles of the arenas and the table that tells a sender where its segment starts
-// in each receiver's ghost tail.  Any failure leaves the NCCL path in place (P2P.on stays false) -- but the
-// decision is all-reduced so that every rank takes the same path.
-int p2p_init(rdc_ctx* c, std::string& err) {
+// in each receiver's ghost tail.
+// Protocol discipline: the three collectives (all-gather of the tables, all-gather of the handles, min all-reduce of
+// the outcome) are issued by EVERY rank in the same order whatever happens locally -- all fallible local work only
+// lowers the rank's `ok` flag -- and the transport is chosen from the all-reduced minimum alone, so the ranks can
+// neither hang in a collective that a peer skipped nor end up on different transports.  The only early returns are
+// hard errors (RDC_E_NOMEM for the 4 KB exchange buffer, RDC_E_COMM when NCCL itself fails): rdc_create fails then.
+// A peer mapping is used for stores and polling loads only (tag-in-word slots, p2p_dev.cuh), which is correct over
+// any cudaIpc peer mapping (NVLink or PCIe); RDC_P2P=0 forces the NCCL transport.
+int p2p_init(rdc_ctx* c, std::string& note) {
   const char* e = getenv("RDC_P2P");
   const int nr = c->S.nranks, me = c->S.rank;
   if (nr < 2 || nr > RDC_MAX_RANKS || (e && atoi(e) == 0)) return 0;
@@ -125,8 +131,9 @@ int p2p_init(rdc_ctx* c, std::string& err) {
   P2P* P = new P2P();
   c->p2p = P;
   const int NSLOT = 8;
-  // table contributed by every rank: {n_owned, vec_len, ghosts received from rank 0..nr-1 (offsets), ok flag}
-  const int TW = nr + 4;
+  // table contributed by every rank: {n_owned, vec_len, ghosts received from rank 0..nr-1 (offsets), spare}
+  const int TW = nr + 4, HW = 64 + 8;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   std::vector<long long> mine((size_t)TW, 0), all((size_t)TW * nr, 0);
   mine[0] = c->S.n_owned;
   mine[1] = (long long)c->S.n_loc * c->nv;
@@ -135,91 +142,90 @@ int p2p_init(rdc_ctx* c, std::string& err) {
     for (size_t k = 0; k < c->S.nbr_rank.size(); k++) off[c->S.nbr_rank[k]] = c->S.recv_ptr[k];
     for (int q = 0; q < nr; q++) mine[2 + q] = off[q];
   }
-  long long* d_tab = nullptr;
-  auto fail = [&](const std::string& why) {
-    err = why;
-    if (d_tab) cudaFree(d_tab);
-    return 0;  // not fatal: NCCL path stays
-  };
-  if (cudaMalloc(&d_tab, sizeof(long long) * TW * (nr + 1)) != cudaSuccess) return fail("p2p: cudaMalloc failed");
+  // one device buffer for all three collectives
+  unsigned char* d_x = nullptr;
+  const size_t xbytes = std::max(sizeof(long long) * TW, (size_t)HW) * (nr + 1);
+  if (cudaMalloc(&d_x, xbytes) != cudaSuccess) { c->err = "p2p: cannot allocate the exchange buffer"; return RDC_E_NOMEM; }
+  auto hard = [&](const char* why) { cudaFree(d_x); c->err = why; return RDC_E_COMM; };
+  // (1) tables
+  long long* d_tab = (long long*)d_x;
   cudaMemcpyAsync(d_tab, mine.data(), sizeof(long long) * TW, cudaMemcpyHostToDevice, c->stream);
   if (c->nccl->AllGather(d_tab, d_tab + TW, (size_t)TW * sizeof(long long), ncclChar, comm, c->stream) != ncclSuccess)
-    return fail("p2p: ncclAllGather failed");
+    return hard("p2p: ncclAllGather failed");
   cudaMemcpyAsync(all.data(), d_tab + TW, sizeof(long long) * TW * nr, cudaMemcpyDeviceToHost, c->stream);
-  cudaStreamSynchronize(c->stream);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return hard("p2p: stream error after the table exchange");
+  // local work: geometry, arena, handle, peer tables -- failures only clear `ok`
+  int ok = 1;
+  std::string why;
+  auto soft = [&](const char* w) { if (ok) why = w; ok = 0; };
   long long max_len = 0;
   for (int q = 0; q < nr; q++) max_len = std::max(max_len, all[(size_t)q * TW + 1]);
   P->slot_bytes = (((size_t)max_len * sizeof(double)) + 255) / 256 * 256;
   P->nslots = NSLOT;
   P->arena_bytes = P->header_bytes + P->slot_bytes * NSLOT;
-  int ok = 1;
-  if ((size_t)c->S.n_ghost * c->nv * 16 > P->slot_bytes) ok = 0;   // staging area of the tagged ghost exchange
-  if (cudaMalloc((void**)&P->arena, P->arena_bytes) != cudaSuccess) { ok = 0; P->arena = nullptr; }
+  if ((size_t)c->S.n_ghost * c->nv * 16 > P->slot_bytes) soft("ghost staging area larger than a vector slot");
+  P->dst_node_off.clear();
+  for (size_t k = 0; k < c->S.nbr_rank.size(); k++) {   // where my segment starts in each neighbour's ghost tail
+    const long long off = all[(size_t)c->S.nbr_rank[k] * TW + 2 + me];
+    if (off < 0 && c->S.send_ptr[k + 1] > c->S.send_ptr[k]) soft("inconsistent neighbour tables");
+    P->dst_node_off.push_back(off < 0 ? 0 : off);
+  }
+  if (cudaMalloc((void**)&P->arena, P->arena_bytes) != cudaSuccess) { cudaGetLastError(); P->arena = nullptr; soft("cudaMalloc of the arena failed"); }
+  if (cudaMalloc((void**)&P->d_peer, sizeof(void*) * nr) != cudaSuccess) { cudaGetLastError(); P->d_peer = nullptr; soft("cudaMalloc failed"); }
+  if (cudaMalloc((void**)&P->d_scratch, sizeof(double) * 8) != cudaSuccess) { cudaGetLastError(); P->d_scratch = nullptr; soft("cudaMalloc failed"); }
   cudaIpcMemHandle_t h;
   memset(&h, 0, sizeof(h));
-  if (ok) {
+  if (P->arena) {
     cudaMemsetAsync(P->arena, 0, P->arena_bytes, c->stream);
-    if (cudaIpcGetMemHandle(&h, P->arena) != cudaSuccess) ok = 0;
+    if (cudaIpcGetMemHandle(&h, P->arena) != cudaSuccess) { cudaGetLastError(); soft("cudaIpcGetMemHandle failed"); }
   }
-  // exchange handles (+ ok flags)
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  const int HW = 64 + 8;
+  // (2) handles (+ the local flag, so that nobody maps an arena of a rank that is giving up)
   std::vector<unsigned char> hmine((size_t)HW, 0), hall((size_t)HW * nr, 0);
   memcpy(hmine.data(), &h, 64);
   hmine[64] = (unsigned char)ok;
-  unsigned char* d_h = nullptr;
-  if (cudaMalloc(&d_h, (size_t)HW * (nr + 1)) != cudaSuccess) return fail("p2p: cudaMalloc failed");
-  cudaMemcpyAsync(d_h, hmine.data(), HW, cudaMemcpyHostToDevice, c->stream);
-  bool gathered = c->nccl->AllGather(d_h, d_h + HW, (size_t)HW, ncclChar, comm, c->stream) == ncclSuccess;
-  cudaMemcpyAsync(hall.data(), d_h + HW, (size_t)HW * nr, cudaMemcpyDeviceToHost, c->stream);
-  cudaStreamSynchronize(c->stream);
-  cudaFree(d_h);
-  if (!gathered) return fail("p2p: ncclAllGather failed");
-  for (int q = 0; q < nr; q++) ok &= hall[(size_t)q * HW + 64];
+  cudaMemcpyAsync(d_x, hmine.data(), HW, cudaMemcpyHostToDevice, c->stream);
+  if (c->nccl->AllGather(d_x, d_x + HW, (size_t)HW, ncclChar, comm, c->stream) != ncclSuccess) return hard("p2p: ncclAllGather failed");
+  cudaMemcpyAsync(hall.data(), d_x + HW, (size_t)HW * nr, cudaMemcpyDeviceToHost, c->stream);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return hard("p2p: stream error after the handle exchange");
+  for (int q = 0; q < nr; q++)
+    if (!hall[(size_t)q * HW + 64]) soft("a peer could not set up its arena");
   P->peer.assign((size_t)nr, nullptr);
   if (ok) {
-    for (int q = 0; q < nr && ok; q++) {
+    for (int q = 0; q < nr; q++) {
       if (q == me) { P->peer[q] = P->arena; continue; }
       cudaIpcMemHandle_t hq;
       memcpy(&hq, hall.data() + (size_t)q * HW, 64);
       if (cudaIpcOpenMemHandle(&P->peer[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         cudaGetLastError();
         P->peer[q] = nullptr;
-        ok = 0;
+        soft("cudaIpcOpenMemHandle of a peer arena failed");
+        break;
       }
     }
   }
-  // every rank must take the same path: min over ranks of the local outcome (re-uses the table buffer)
+  // (3) every rank takes the same path: min over the ranks of the local outcome
   {
     long long v = ok;
     cudaMemcpyAsync(d_tab, &v, sizeof(long long), cudaMemcpyHostToDevice, c->stream);
-    // ncclMin on int64
-    bool r = c->nccl->AllReduce(d_tab, d_tab, 1, ncclInt64, ncclMin, comm, c->stream) == ncclSuccess;
+    if (c->nccl->AllReduce(d_tab, d_tab, 1, ncclInt64, ncclMin, comm, c->stream) != ncclSuccess) return hard("p2p: ncclAllReduce failed");
     cudaMemcpyAsync(&v, d_tab, sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
-    cudaStreamSynchronize(c->stream);
-    ok = r ? (int)v : 0;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return hard("p2p: stream error after the outcome exchange");
+    if (ok && !v) why = "a peer failed to map the arenas";
+    ok = (int)v;
   }
-  cudaFree(d_tab);
-  d_tab = nullptr;
-  if (!ok) return fail("p2p: cudaIpc mapping of a peer arena failed; NCCL send/recv stays in use");
-  // where my segment starts in each neighbour's ghost tail
-  P->dst_node_off.clear();
-  for (size_t k = 0; k < c->S.nbr_rank.size(); k++) {
-    const int q = c->S.nbr_rank[k];
-    const long long n_owned_q = all[(size_t)q * TW + 0], off = all[(size_t)q * TW + 2 + me];
-    if (off < 0 && c->S.send_ptr[k + 1] > c->S.send_ptr[k]) return fail("p2p: inconsistent neighbour tables");
-    (void)n_owned_q;
-    P->dst_node_off.push_back(off < 0 ? 0 : off);
+  cudaFree(d_x);
+  if (!ok) {   // agreed by all ranks: NCCL send/recv and all-reduce stay in use
+    for (int q = 0; q < nr; q++)
+      if (q != me && P->peer[q]) { cudaIpcCloseMemHandle(P->peer[q]); P->peer[q] = nullptr; }
+    cudaFree(P->arena); cudaFree(P->d_peer); cudaFree(P->d_scratch);
+    P->arena = nullptr; P->d_peer = nullptr; P->d_scratch = nullptr;
+    P->peer.clear();
+    note = "p2p off (" + why + "); NCCL transport";
+    return 0;
   }
-  // two staging areas for the tagged ghost exchange (16 B per ghost value), one per parity
-  for (int par = 0; par < 2; par++) {
-    double* sp = p2p_alloc_raw(P);
-    if (!sp) return fail("p2p: arena too small for the ghost staging areas");
-    P->stage_off[par] = (size_t)((unsigned char*)sp - P->arena);
-  }
-  if (cudaMalloc((void**)&P->d_peer, sizeof(void*) * nr) != cudaSuccess) return fail("p2p: cudaMalloc failed");
+  // two staging areas for the tagged ghost exchange (16 B per ghost value), one per parity: NSLOT >= 2 by construction
+  for (int par = 0; par < 2; par++) P->stage_off[par] = (size_t)((unsigned char*)p2p_alloc_raw(P) - P->arena);
   cudaMemcpyAsync(P->d_peer, P->peer.data(), sizeof(void*) * nr, cudaMemcpyHostToDevice, c->stream);
-  if (cudaMalloc((void**)&P->d_scratch, sizeof(double) * 8) != cudaSuccess) return fail("p2p: cudaMalloc failed");
   cudaMemsetAsync(P->d_scratch, 0, sizeof(double) * 8, c->stream);
   cudaStreamSynchronize(c->stream);
   P->on = true;

@@ -117,7 +117,11 @@ int p2p_check_error(rdc_ctx* c) {
   int e = 0;
   RDC_CUDA(cudaMemcpyAsync(&e, &((P2PHeader*)P->arena)->error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
-  if (e) { c->err = "peer-memory exchange timed out (a rank did not arrive)"; return RDC_E_COMM; }
+  if (e) {   // report once: the flag is cleared so that a later, healthy exchange is not blamed for it
+    RDC_CUDA(cudaMemsetAsync(&((P2PHeader*)P->arena)->error, 0, sizeof(int), c->stream));
+    c->err = "peer-memory exchange timed out (a rank did not arrive); ghost values are stale";
+    return RDC_E_COMM;
+  }
   return 0;
 }
 

@@ -32,12 +32,28 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsign
   return true;
 }
 
-// One ghost exchange with the tag-in-word protocol: every value travels as a 16-byte word {bits of the double,
-// sequence number} written by ONE vector store straight into the receiver's staging area (NVLink peer memory); the
-// receiver polls each word until it carries the current sequence number and moves the value into the ghost tail of
-// its vector.  Data and "flag" arrive together: no fences, no flag round trip, no pack buffer.  Staging is
-// double-buffered by the parity of the sequence number (a sender can be at most one exchange ahead of a receiver
-// because it needs the receiver's data of the previous exchange to finish its own kernel).
+// One ghost exchange with the tag-in-word protocol: every value travels as a 16-byte slot of two 8-byte words, each
+// {32 data bits | 32-bit tag = low half of the sequence number}, written straight into the receiver's staging area
+// (NVLink peer memory); the receiver polls the slot until BOTH words carry the current tag and moves the value into
+// the ghost tail of its vector.  PTX guarantees single-copy atomicity only per 8-byte word (a vector store may be
+// performed as two scalar stores, on NVLink as on PCIe peer mappings), so every word carries its own tag: a torn or
+// reordered slot can never be mistaken for a complete one.  Data and "flag" arrive together: no fences, no flag
+// round trip, no pack buffer.  Staging is double-buffered by the parity of the sequence number (a sender can be at
+// most one exchange ahead of a receiver because it needs the receiver's data of the previous exchange to finish its
+// own kernel); a slot is reused every second exchange, 2^33 exchanges before a tag could repeat in it.
+__device__ __forceinline__ void tag_store(ulonglong2* slot, double v, unsigned tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (b & 0xffffffffull) | ((unsigned long long)tag << 32);
+  const unsigned long long w1 = (b >> 32) | ((unsigned long long)tag << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool tag_load(const ulonglong2* slot, unsigned tag, double* v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  if ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) return false;
+  *v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return true;
+}
 struct HaloArgs {
   ulonglong2* dst[RDC_MAX_RANKS];             // neighbour k: where MY values go inside ITS staging area (this parity)
   const ulonglong2* src;                      // my own staging area (this parity)
@@ -56,26 +72,23 @@ __device__ __forceinline__ void halo_exchange_block(const HaloArgs& A, int k, in
                                                     unsigned long long seq, P2PHeader* hdr, F val) {
   const int s0 = A.send_ptr[k], scnt = (A.send_ptr[k + 1] - s0) * nv;
   ulonglong2* dst = A.dst[k];
+  const unsigned tag = (unsigned)seq;
   for (int i = b * blockDim.x + threadIdx.x; i < scnt; i += nb * blockDim.x) {
     const int node = i / nv, a = i - node * nv;
-    const double v = val((size_t)send_idx[s0 + node] * nv + a);
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + i), "l"((unsigned long long)__double_as_longlong(v)),
-                 "l"(seq)
-                 : "memory");
+    tag_store(dst + i, val((size_t)send_idx[s0 + node] * nv + a), tag);
   }
   const int r0 = A.recv_ptr[k] * nv, rcnt = (A.recv_ptr[k + 1] - A.recv_ptr[k]) * nv;
   const ulonglong2* src = A.src + r0;
   double* ghost = x + (size_t)A.n_owned * nv + r0;
   for (int i = b * blockDim.x + threadIdx.x; i < rcnt; i += nb * blockDim.x) {
-    unsigned long long w0, w1;
+    double v = 0.0;
     const unsigned long long t0 = global_ns();
     int spins = 0;
-    for (;;) {
-      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src + i) : "memory");
-      if (w1 == seq) break;
+    bool got;
+    while (!(got = tag_load(src + i, tag, &v))) {
       if ((++spins & 1023) == 0 && global_ns() - t0 > P2P_TIMEOUT_NS) { hdr->error = 1; break; }
     }
-    ghost[i] = __longlong_as_double((long long)w0);
+    if (got) ghost[i] = v;   // after a timeout the ghost keeps its old value; the host reports RDC_E_COMM
   }
 }
 

@@ -224,7 +224,7 @@ static int finish(rdc_ctx* c, double* host_out) {
   if (rc) return rc;
   RDC_CUDA(cudaMemcpyAsync(host_out, R->d_out, (size_t)R->n_regions * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return p2p_check_error(c);   // the ghost exchange / all-reduce above may have timed out on a missing peer
 }
 
 int region_volumes(rdc_ctx* c, int ncond, const rdc_range_cond* cond, double* vol) {

@@ -568,6 +568,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
     const int per_sm_env = c->opt.tma_ctas_per_sm, stages_env = c->opt.tma_stages;
     const int per_sm = per_sm_env > 0 ? per_sm_env : (c->nv == 3 ? 6 : 2);  // measured: 2 stages x 6 CTAs/SM beats 3 x 4 by 16 %
     unsigned tg = (unsigned)(W->n_tiles < 148 * per_sm ? W->n_tiles : 148 * per_sm);
+    if (tg > (unsigned)SPMV_MAX_GRID) tg = SPMV_MAX_GRID;   // W->partial holds 2 * SPMV_MAX_GRID per-CTA partials
 #define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
     int trc;
     switch (c->model) {
@@ -864,7 +865,10 @@ int launch_clamp(rdc_ctx* c) {
     c->ripf_primed = true;
     if (mx <= 0.0) { c->err = "RT_total_max <= 0 (ripf.C:773)"; return RDC_E_MODEL; }
     // ghosts of TD are needed by the next assembly
-    if (c->S.nranks > 1) { rc = halo_exchange(c, c->d_td); if (rc) return rc; }
+    if (c->S.nranks > 1) {
+      if ((rc = halo_exchange(c, c->d_td))) return rc;
+      if ((rc = p2p_check_error(c))) return rc;   // synchronises; the next assembly reads the TD ghosts
+    }
     return 0;
   }
   const size_t n = (size_t)c->S.n_owned * c->nv;
@@ -1004,7 +1008,7 @@ static int poll(rdc_ctx* c) {
   RDC_CUDA(cudaMemcpyAsync(W->h_state, W->state, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaMemcpyAsync(W->h_scal, W->scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return p2p_check_error(c);   // a timed-out peer exchange surfaces at every host synchronisation of every solver
 }
 
 // GMRES(m), left Jacobi (or no) preconditioning.  x = c->d_u (initial guess and result), b = c->d_rhs.
@@ -1401,7 +1405,6 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
     RDC_CUDA(cudaGetLastError());
   }
   if ((rc = poll(c))) return rc;
-  if ((rc = p2p_check_error(c))) return rc;
   *its_out = W->h_state[1];
   *res_out = W->h_scal[S_RES];
   c->st.resnorm0 = W->h_scal[S_BNORM];
@@ -1418,6 +1421,8 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
     return RDC_E_ARG;
   }
   if (restart < 1) restart = 30;
+  if (restart > 500) { c->err = "rdc_solve: restart must be <= 500 (the Gram-Schmidt coefficients share a 512-entry buffer)"; return RDC_E_ARG; }
+  if (maxits < 0) { c->err = "rdc_solve: maxits must be >= 0"; return RDC_E_ARG; }
   SolverWork* W = c->work;
   W->n_ev_used = 0;
   int rc;

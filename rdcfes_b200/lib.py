@@ -29,12 +29,12 @@ class Stats(C.Structure):
                 ("bytes_index", C.c_int64), ("kernel_launches", C.c_int64), ("ripf_rt_total_max", C.c_int),
                 ("sum_ms_assemble", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_clamp", C.c_double),
                 ("sum_ms_spmv", C.c_double), ("sum_iterations", C.c_int64), ("sum_n_spmv", C.c_int64),
-                ("n_solves", C.c_int64)]
+                ("n_solves", C.c_int64), ("p2p_on", C.c_int), ("p2p_fused", C.c_int)]
 
 
 EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_distributed", "rdc_comm_unique_id",
            "rdc_destroy", "rdc_last_error", "rdc_set_params", "rdc_set_elem_field", "rdc_set_nodal_field",
-           "rdc_update_coords", "rdc_set_solution", "rdc_get_solution", "rdc_get_solution_owned", "rdc_get_old_solution", "rdc_n_dofs",
+           "rdc_update_coords", "rdc_set_solution", "rdc_get_solution", "rdc_get_solution_owned", "rdc_get_old_solution", "rdc_get_rhs", "rdc_n_dofs",
            "rdc_set_time", "rdc_set_dt", "rdc_rotate", "rdc_assemble", "rdc_solve", "rdc_clamp", "rdc_step",
            "rdc_spmv", "rdc_bench_spmv", "rdc_bench_stream", "rdc_download_csr", "rdc_free", "rdc_get_stats", "rdc_set_stream",
            "rdc_version", "rdc_probe_partition", "rdc_set_option", "rdc_set_subdomains", "rdc_region_volumes",
@@ -73,7 +73,7 @@ def load():
         "rdc_comm_unique_id": [vp],
         "rdc_set_params": [vp, vp, i32], "rdc_set_elem_field": [vp, i32, vp, i32],
         "rdc_set_nodal_field": [vp, i32, vp, i32], "rdc_update_coords": [vp, vp],
-        "rdc_set_solution": [vp, vp], "rdc_get_solution": [vp, vp], "rdc_get_solution_owned": [vp, vp], "rdc_get_old_solution": [vp, vp],
+        "rdc_set_solution": [vp, vp], "rdc_get_solution": [vp, vp], "rdc_get_solution_owned": [vp, vp], "rdc_get_old_solution": [vp, vp], "rdc_get_rhs": [vp, vp],
         "rdc_set_time": [vp, f64], "rdc_set_dt": [vp, f64], "rdc_rotate": [vp], "rdc_assemble": [vp, f64, f64],
         "rdc_solve": [vp, i32, i32, f64, i32, i32, C.POINTER(i32), C.POINTER(f64)],
         "rdc_clamp": [vp],

@@ -187,6 +187,12 @@ class TransientRdcSystem:
         return mean
 
     # ------------------------------------------------------------------ parity / measurement
+    def get_rhs(self):
+        """system.rhs after the assemble callback (global dof order)."""
+        f = np.empty(self.n_dofs)
+        self._check(self._L.rdc_get_rhs(self._h, _ptr(f)))
+        return f
+
     def spmv(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.empty(self.n_dofs)

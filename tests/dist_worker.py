@@ -24,18 +24,25 @@ def main():
     from rdcfes_b200 import system as rs
     buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
     failures = []
-    for model, ksp, partitioner, nsteps in ((cases.ADPM, 0, 0, 3), (cases.PIHNA, 0, 1, 2), (cases.RIPF, 2, 0, 12),
-                                            (cases.HCC, 2, 1, 2)):
+    # mesh large enough that every rank owns more nodes than it has ghosts (the peer-memory staging area needs that)
+    n = {2: 7, 4: 10}.get(world, 12)
+    # BASELINE.json configs: RIPF on 2 ranks (BiCGStab here), coupled_hcc with GMRES on 4 ranks (ksp 0 = GMRES(30))
+    for model, ksp, partitioner, nsteps in ((cases.ADPM, 2, 0, 3), (cases.PIHNA, 0, 1, 2), (cases.RIPF, 2, 0, 12),
+                                            (cases.HCC, 0, 1, 2)):
         if rank == 0:
             buf.copy_(torch.frombuffer(bytearray(rs.make_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, 0)
         uid = bytes(buf.cpu().numpy().tobytes())
         length = 50.0 if model == cases.RIPF else 1.0
-        conn, xyz = cases.mesh(cases.TET4, 7, distort=0.2, length=length)
+        conn, xyz = cases.mesh(cases.TET4, n, distort=0.2, length=length)
         p, u0, ef, nf = cases.case(model, conn, xyz, "full")
         gpu = cases.gpu_system(model, cases.TET4, conn, xyz, p, u0, ef, nf, device=local, rank=rank, nranks=world,
                                partitioner=partitioner, unique_id=uid)
         gpu.ksp = ksp
+        st = gpu.stats()
+        if not (st.p2p_on and st.p2p_fused) and os.environ.get("RDC_P2P", "1") != "0":
+            failures.append(f"{cases.NAMES[model]}: the NVLink peer-memory path is not active on rank {rank} "
+                            f"(p2p_on={st.p2p_on}, fused={st.p2p_fused}): the test would only exercise the NCCL fallback")
         orc = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf) if rank == 0 else None
         dt = cases.DT[model]
         # operator rows owned by this rank against the oracle (every rank checks its own rows)
@@ -52,9 +59,9 @@ def main():
                 failures.append(f"{cases.NAMES[model]}: pattern of row {r}")
                 break
         ref = np.concatenate([val_o[o2.rowptr[r]:o2.rowptr[r + 1]] for r in rows])
-        if (np.abs(val - ref) / cases.csr_tolerance(val_o)[: 1].max()).max() > 1.0 and \
-                (np.abs(val - ref) > 1e-12 * np.maximum(np.abs(ref), 1e-3 * np.abs(val_o).max())).any():
-            failures.append(f"{cases.NAMES[model]}: K rows differ on rank {rank}")
+        tol = 1e-12 * np.maximum(np.abs(ref), 1e-3 * np.abs(val_o).max())   # cases.csr_tolerance, row subset
+        if (np.abs(val - ref) > tol).any():
+            failures.append(f"{cases.NAMES[model]}: K rows differ on rank {rank}: worst {(np.abs(val - ref) / tol).max():.2e} x tol")
         if np.abs(rhs - rhs_o[rows]).max() > 1e-12 * np.abs(rhs_o).max():
             failures.append(f"{cases.NAMES[model]}: F differs on rank {rank}")
         trace = []

@@ -314,15 +314,55 @@ def test_full_size_properties(n):
     gpu.rtol = 1e-13
     gpu.linear_solve()
     assert np.linalg.norm(gpu.get_solution() - u0.ravel()) <= 1e-9 * np.linalg.norm(u0)
-    # P-full step, then the true residual through the device operator
+    # P-full step without the clamp, then the TRUE residual F - K u through the device operator (rdc_spmv, rdc_get_rhs)
     gpu.set_parameters(cases.synth.adpm_params("full"))
     gpu.set_solution(u0)
     gpu.rtol = 1e-12
-    its, res = gpu.step(0.05)
+    gpu.time = 0.05
+    gpu.rotate()
+    gpu.assemble(0.05, 0.05)
+    its, res = gpu.linear_solve()
     u1 = gpu.get_solution()
+    F = gpu.get_rhs()
+    r = F - gpu.spmv(u1)
+    rel = np.linalg.norm(r) / np.linalg.norm(F)
     st = gpu.stats()
-    print(f"n={n}: its {its}, assemble {st.ms_assemble:.3f} ms, solve {st.ms_solve:.2f} ms")
-    assert 0 < its < 500 and (u1 >= 0).all()
+    print(f"n={n}: its {its}, assemble {st.ms_assemble:.3f} ms, solve {st.ms_solve:.2f} ms, true residual {rel:.2e}")
+    assert 0 < its < 500
+    assert rel <= 1e-10, rel
+    gpu.check_solution()
+    assert (gpu.get_solution() >= 0).all()
+    gpu.close()
+
+
+@pytest.mark.parametrize("model,n", [(ADPM, 48), (PIHNA, 40)])
+def test_mid_size_step_vs_oracle(model, n):
+    """663 552 (ADPM) / 384 000 (PIHNA) tets: large enough that every assembly CTA shape, SpMV tile shape and the
+    multi-wave grids are exercised, small enough that the oracle answers in seconds.  One full step of the time loop
+    on both sides: K/F through checksums and the new state to 1e-8."""
+    from oracle import oracle as O
+    conn, xyz = cases.mesh(TET4, n, distort=0.15, length=_length(model))
+    p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+    orc = cases.oracle_problem(model, TET4, conn, xyz, p, u0, ef, nf, nthreads=8)
+    gpu = cases.gpu_system(model, TET4, conn, xyz, p, u0, ef, nf)
+    dt = cases.DT[model]
+    orc.u_old = orc.u.copy()
+    val_o, rhs_o = orc.assemble(dt, dt)
+    gpu.rotate()
+    gpu.assemble(dt, dt)
+    F = gpu.get_rhs()
+    assert np.abs(F - rhs_o).max() <= 1e-12 * np.abs(rhs_o).max()
+    for seed in (1, 2):   # K through its action on random vectors (the full CSR download is tested at small sizes)
+        x = np.random.default_rng(seed).normal(size=orc.D)
+        y_o, y_g = orc.spmv(x), gpu.spmv(x)
+        assert np.linalg.norm(y_g - y_o) <= 1e-12 * np.linalg.norm(y_o)
+    gpu.time = 0.0
+    orc.step(dt, pc=O.PC_ILU)
+    its, res = gpu.step(dt)
+    u = gpu.get_solution()
+    rel = np.linalg.norm(u - orc.u) / np.linalg.norm(orc.u)
+    print(f"{cases.NAMES[model]} n={n}: its {its}, rel L2 vs oracle {rel:.2e}")
+    assert rel <= 1e-8
     gpu.close()
 
 
