@@ -147,18 +147,19 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     if ((r = upload(c, &c->d_rowptr, S.rowptr))) return r;
     if ((r = upload(c, &c->d_col, S.col))) return r;
     if ((r = upload(c, &c->d_diag_blk, S.diag_blk))) return r;
-    {  // 32-byte CTA descriptors {node0, nnode, pair0, npairs, blk0, nblk, contributor base, 0}
+    {  // 48-byte CTA descriptors {node0, nnode, pair0, npairs | blk0, nblk, contributor base, first task | ntask, 0, 0, 0}
       const int32_t nc = (int32_t)S.cta_node.size() - 1;
-      std::vector<int32_t> desc((size_t)nc * 8, 0);
+      std::vector<int32_t> desc((size_t)nc * 12, 0);
       for (int32_t k = 0; k < nc; k++) {
         const int32_t a = S.cta_node[k], b = S.cta_node[k + 1];
-        int32_t* d = desc.data() + (size_t)k * 8;
+        int32_t* d = desc.data() + (size_t)k * 12;
         d[0] = a; d[1] = b - a; d[2] = S.n2e_ptr[a]; d[3] = S.n2e_ptr[b] - S.n2e_ptr[a];
         d[4] = S.rowptr[a]; d[5] = S.rowptr[b] - S.rowptr[a]; d[6] = S.cptr[S.rowptr[a]];
+        d[7] = S.task_ptr[k]; d[8] = S.task_ptr[k + 1] - S.task_ptr[k];
       }
       if ((r = upload(c, &c->d_cta_node, desc))) return r;
     }
-    if ((r = upload(c, &c->d_cptr, S.cptr))) return r;
+    if ((r = upload(c, &c->d_task, S.task))) return r;
     if ((r = upload(c, &c->d_clist, S.clist))) return r;
     c->ncta = (int)S.cta_node.size() - 1;
     c->nnzb = S.rowptr[S.n_owned];
@@ -207,12 +208,13 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     const int64_t nkv = c->nkv;
     c->st.bytes_assemble = 4LL * c->nen * El + 24LL * Nl + 8LL * nv * Nl + 8LL * f_e * El + 8LL * f_n * Nl + 8LL * nkv * nnzb + 8LL * nv * No;
     c->st.bytes_spmv = nnzb * (8LL * nkv + 4) + 4LL * (No + 1) + 16LL * nv * No;
-    c->st.bytes_index = 4LL * (int64_t)S.pair.size() + 4LL * (No + 1) * 2 + 32LL * ((int64_t)S.cta_node.size() - 1) + 4LL * (nnzb + 1) +
+    c->st.bytes_index = 4LL * (int64_t)S.pair.size() + 4LL * (No + 1) * 2 + 48LL * ((int64_t)S.cta_node.size() - 1) + 4LL * (int64_t)S.task.size() +
                         2LL * (int64_t)S.clist.size();
     c->st.n_nodes_local = No; c->st.n_nodes_ghost = S.n_ghost; c->st.n_elems_local = El; c->st.nnzb_local = nnzb;
   }
   // the host copies of the big maps are no longer needed
   std::vector<int32_t>().swap(S.pair); std::vector<int32_t>().swap(S.cptr); std::vector<uint16_t>().swap(S.clist);
+  std::vector<int32_t>().swap(S.task);
   std::vector<int32_t>().swap(S.conn);
   *out = c;
   return RDC_OK;
@@ -245,7 +247,7 @@ extern "C" void rdc_destroy(rdc_ctx* c) {
   if (p2p_owns(c, c->d_td)) c->d_td = nullptr;
   comm_destroy(c);
   cudaFree(c->d_conn); cudaFree(c->d_xyz); cudaFree(c->d_efield); cudaFree(c->d_n2e_ptr); cudaFree(c->d_pair);
-  cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_diag_blk); cudaFree(c->d_cta_node); cudaFree(c->d_cptr);
+  cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_diag_blk); cudaFree(c->d_cta_node); cudaFree(c->d_task);
   cudaFree(c->d_clist); cudaFree(c->d_dofmap); cudaFree(c->d_val); cudaFree(c->d_rhs); cudaFree(c->d_dinv);
   cudaFree(c->d_u); cudaFree(c->d_uold); cudaFree(c->d_uolder); cudaFree(c->d_stage); cudaFree(c->d_td); cudaFree(c->d_rt);
   cudaFree(c->d_prev); cudaFree(c->d_aux); cudaFree(c->d_send_idx); cudaFree(c->d_sendbuf);

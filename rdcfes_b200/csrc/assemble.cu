@@ -10,9 +10,12 @@
 //   * phase 1: each thread gathers its element (connectivity, padded coordinates, old solution, element
 //     and nodal aux fields), evaluates geometry + the model's coefficient table at the quadrature points
 //     and forms ITS ROW of Ke (nen blocks of v x v) and of Fe in registers; rows go to shared memory.
-//   * phase 2: one thread per block of the CTA's rows sums the staged contributions in the fixed order of
-//     a precomputed contributor list (ascending element id == the reference's serial loop order) and
-//     writes every value of K exactly once, coalesced.  No float atomics; bit-reproducible.
+//   * phase 2: the staged contributions of every block of the CTA's rows are added in the fixed order of a
+//     precomputed contributor list (ascending element id) and every value of K is written exactly once,
+//     coalesced.  The work list is cut into TASKS of at most 8 (16) contributors -- a diagonal block has 24 and
+//     more contributors, an off-diagonal one ~6, and a warp runs as long as its longest lane -- the pieces of a
+//     split block leave partial sums in shared memory that the first piece adds in piece order.  No float
+//     atomics; the summation order is fixed by the set-up, so two assemblies are bit-identical.
 // Operator layout ("row-local SoA"): block row i has L_i blocks; only the NKV structurally non-zero entries
 // (a,b) of the model's v x v node block are stored (KMASK); entry plane s = rank of bit a*v+b in KMASK:
 //   val[rowptr[i]*NKV + s*L_i + k]   so that a half-warp reading one row is fully coalesced.
@@ -45,7 +48,7 @@ struct AsmArgs {
   const int32_t* pair;
   const int32_t* rowptr;
   const int32_t* cta_node;
-  const int32_t* cptr;
+  const int2* task;
   const uint16_t* clist;
   const int32_t* diag_blk;
   double* val;
@@ -134,20 +137,24 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   __shared__ int s_rowptr[PAIRS + 1];
   __shared__ int s_n2e[PAIRS + 1];
   __shared__ int s_diag[PAIRS];
-  __shared__ int s_cptr[PAIRS * NEN + 1];            // contributor offsets of the CTA's blocks (relative)
   __shared__ __align__(4) unsigned short s_clist_raw[PAIRS * NEN + 4];  // contributor codes j*PAIRS + pair (offset in a stage slot)
+  __shared__ double s_part[RDC_ASM_MAX_SPLIT * (NKV > 0 ? NKV : 1)];   // partial sums of the pieces of split blocks
 
   const int tid = threadIdx.x;
-  // one 32-byte descriptor per CTA: a single load level instead of the chain cta_node -> n2e_ptr -> rowptr -> cptr
-  const int4 d0 = reinterpret_cast<const int4*>(A.cta_node)[2 * (size_t)blockIdx.x];
-  const int4 d1 = reinterpret_cast<const int4*>(A.cta_node)[2 * (size_t)blockIdx.x + 1];
+  // one 48-byte descriptor per CTA: a single load level instead of the chain cta_node -> n2e_ptr -> rowptr -> lists
+  const int4 d0 = reinterpret_cast<const int4*>(A.cta_node)[3 * (size_t)blockIdx.x];
+  const int4 d1 = reinterpret_cast<const int4*>(A.cta_node)[3 * (size_t)blockIdx.x + 1];
+  const int ntask = A.cta_node[12 * (size_t)blockIdx.x + 8];
   const int node0 = d0.x, nnode = d0.y, pair0 = d0.z, npairs = d0.w;
-  const int blk0 = d1.x, nblk = d1.y;
+  const int task0 = d1.w;
+  // my phase-2 task: fetched now, used after phase 1 (its latency disappears behind the element work)
+  int2 my_task = make_int2(0, 0);
+  if (tid < ntask) my_task = __ldg(A.task + task0 + tid);
   // Index prologue: everything phase 2 needs goes to shared memory with cp.async (LDGSTS), i.e. without passing
   // through registers -- the warps do not wait for these loads before they start phase 1 (the plain load+store
   // version accounted for 18 % of the kernel's stall samples).  Raw values are stored; the CTA-relative offsets
-  // (pair0, c_base) are subtracted where they are used.  The uint16 contributor list is copied as 4-byte words
-  // from the aligned-down address.
+  // are subtracted where they are used.  The uint16 contributor list is copied as 4-byte words from the
+  // aligned-down address.
   const int c_base = d1.z;
   const unsigned short* s_clist = s_clist_raw + (c_base & 1);
   {
@@ -156,7 +163,6 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
     };
     for (int r = tid; r <= nnode; r += PAIRS) { cp4(&s_rowptr[r], A.rowptr + node0 + r); cp4(&s_n2e[r], A.n2e_ptr + node0 + r); }
     for (int r = tid; r < nnode; r += PAIRS) cp4(&s_diag[r], A.diag_blk + node0 + r);
-    for (int b = tid; b <= nblk; b += PAIRS) cp4(&s_cptr[b], A.cptr + blk0 + b);
     const int n_w = (npairs * NEN + (c_base & 1) + 1) / 2;
     const unsigned* src_w = reinterpret_cast<const unsigned*>(A.clist + (c_base & ~1));
     for (int i = tid; i < n_w; i += PAIRS) cp4(reinterpret_cast<unsigned*>(s_clist_raw) + i, src_w + i);
@@ -375,40 +381,65 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
-  // ------------------------------------------------------------------ phase 2: one block per thread
-  // Each block is the fixed-order sum of its contributors (ascending element id == the reference's serial loop
-  // order) and is written exactly once; consecutive threads write consecutive blocks of a row (row-local SoA).
-  for (int b = tid; b < nblk; b += PAIRS) {
-    const int B = blk0 + b;
-    int lo = 0, hi = nnode;  // largest r with s_rowptr[r] <= B
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_rowptr[mid] <= B) lo = mid; else hi = mid;
-    }
-    const int r0 = s_rowptr[lo], L = s_rowptr[lo + 1] - r0, kk = B - r0;
-    double acc[NKV > 0 ? NKV : 1];
-#pragma unroll
-    for (int s = 0; s < NKV; s++) acc[s] = 0.0;
-    const int c1 = s_cptr[b + 1] - c_base;
-    for (int c = s_cptr[b] - c_base; c < c1; c++) {
-      const double* src = stageK + s_clist[c];
-#pragma unroll
-      for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * NEN * PAIRS];
-    }
-    double* dst = A.val + (size_t)r0 * NKV + kk;
-#pragma unroll
-    for (int s = 0; s < NKV; s++) dst[(size_t)s * L] = acc[s];
-    if (B == s_diag[lo]) {  // point Jacobi: every model has C[a][a] in its mask
-#pragma unroll
-      for (int a = 0; a < NV; a++) A.dinv[(size_t)(node0 + lo) * NV + a] = 1.0 / acc[slot_of(KMASK, a * NV + a)];
-    }
-  }
+  // ------------------------------------------------------------------ phase 2: one task per thread
+  // load vector first (one thread per owned dof, pairs of the node in ascending element order)
   for (int t = tid; t < nnode * NV; t += PAIRS) {
     const int r = t / NV, a = t - r * NV;
     const int q0 = s_n2e[r] - pair0, q1 = s_n2e[r + 1] - pair0;
     double f = 0.0;
     for (int q = q0; q < q1; q++) f += stageF[a * PAIRS + q];
     A.rhs[(size_t)(node0 + r) * NV + a] = f;
+  }
+  // a finished block: plane s of block kk of row r goes to val[rowptr[r]*NKV + s*L + kk] (row-local SoA); the thread
+  // that finishes a diagonal block also writes the point-Jacobi scaling (every model has C[a][a] in its mask)
+  auto write_block = [&](int r, int kk, const double* acc) {
+    const int r0 = s_rowptr[r], L = s_rowptr[r + 1] - r0;
+    double* dst = A.val + (size_t)r0 * NKV + kk;
+#pragma unroll
+    for (int s = 0; s < NKV; s++) dst[(size_t)s * L] = acc[s];
+    if (r0 + kk == s_diag[r]) {
+#pragma unroll
+      for (int a = 0; a < NV; a++) A.dinv[(size_t)(node0 + r) * NV + a] = 1.0 / acc[slot_of(KMASK, a * NV + a)];
+    }
+  };
+  bool any_split = false;
+  for (int t = tid; t < ntask; t += PAIRS) {
+    const int2 tk = t == tid ? my_task : __ldg(A.task + task0 + t);
+    const unsigned x = (unsigned)tk.x, y = (unsigned)tk.y;
+    const int c0 = (int)(x >> 16), cnt = (int)(y & 0xffu), np = (int)((y >> 16) & 0xffu);
+    double acc[NKV > 0 ? NKV : 1];
+#pragma unroll
+    for (int s = 0; s < NKV; s++) acc[s] = 0.0;
+    for (int c = c0; c < c0 + cnt; c++) {
+      const double* src = stageK + s_clist[c];
+#pragma unroll
+      for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * NEN * PAIRS];
+    }
+    if (np == 1) {
+      write_block((int)(x & 0xffu), (int)((x >> 8) & 0xffu), acc);
+    } else {
+      any_split = true;
+      double* ps = s_part + (size_t)(y >> 24) * NKV;
+#pragma unroll
+      for (int s = 0; s < NKV; s++) ps[s] = acc[s];
+    }
+  }
+  if (__syncthreads_or(any_split)) {   // the first piece of a split block adds the partial sums in piece order
+    for (int t = tid; t < ntask; t += PAIRS) {
+      const int2 tk = t == tid ? my_task : __ldg(A.task + task0 + t);
+      const unsigned x = (unsigned)tk.x, y = (unsigned)tk.y;
+      const int np = (int)((y >> 16) & 0xffu);
+      if (np == 1 || ((y >> 8) & 0xffu) != 0u) continue;
+      const double* ps = s_part + (size_t)(y >> 24) * NKV;
+      double acc[NKV > 0 ? NKV : 1];
+#pragma unroll
+      for (int s = 0; s < NKV; s++) acc[s] = ps[s];
+      for (int k = 1; k < np; k++) {
+#pragma unroll
+        for (int s = 0; s < NKV; s++) acc[s] += ps[(size_t)k * NKV + s];
+      }
+      write_block((int)(x & 0xffu), (int)((x >> 8) & 0xffu), acc);
+    }
   }
 }
 
@@ -476,7 +507,7 @@ int launch_assemble(rdc_ctx* c) {
   A.conn = c->d_conn; A.xyz4 = c->d_xyz; A.u_old = c->d_uold; A.efield = c->d_efield;
   A.aux0 = nullptr; A.aux1 = nullptr;
   A.n2e_ptr = c->d_n2e_ptr; A.pair = c->d_pair; A.rowptr = c->d_rowptr; A.cta_node = c->d_cta_node;
-  A.cptr = c->d_cptr; A.clist = c->d_clist; A.diag_blk = c->d_diag_blk; A.val = c->d_val; A.rhs = c->d_rhs; A.dinv = c->d_dinv;
+  A.task = reinterpret_cast<const int2*>(c->d_task); A.clist = c->d_clist; A.diag_blk = c->d_diag_blk; A.val = c->d_val; A.rhs = c->d_rhs; A.dinv = c->d_dinv;
   const double* p = c->params.data();
   const double h = c->dt / 2.0;
   switch (c->model) {

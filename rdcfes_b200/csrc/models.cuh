@@ -98,20 +98,28 @@ struct Adpm {
                                                     const double (*GA)[3], double (*dir)[3]) {
     (void)GA;
     for (int d = 0; d < 3; d++) { dir[0][d] = G[1][d]; dir[1][d] = G[2][d]; dir[2][d] = 0.0; dir[3][d] = 0.0; }
-    const double nA = sqrt(dot3_rn(G[1], G[1]));
-    const double nT = sqrt(dot3_rn(G[2], G[2]));
-    if (nA != 0.0) {
-      const double u[3] = {G[1][0] / nA, G[1][1] / nA, G[1][2] / nA};
-      const double d = dot3_rn(u, ef);
-      if (d > +p.omega_A) { dir[2][0] = ef[0]; dir[2][1] = ef[1]; dir[2][2] = ef[2]; }
-      else if (d < -p.omega_A) { dir[2][0] = -ef[0]; dir[2][1] = -ef[1]; dir[2][2] = -ef[2]; }
+    align(G[1], ef, p.omega_A, dir[2]);
+    align(G[2], ef, p.omega_T, dir[3]);
+  }
+  // adpm.C:473-492: tract direction +ef / -ef / 0 from d = (g/|g|) . ef against +-omega.  The reference's expression
+  // (unit vector by three divisions, ordered dot product) costs a square root and three divisions; d is first
+  // estimated as (g . ef) / |g| from one reciprocal square root, and only when that estimate is within 1e-11 of a
+  // threshold (relative to |ef| + omega: thousands of times the rounding error of either expression) is the
+  // reference's own sequence evaluated, so the decision is always the one the reference takes.
+  __device__ static __forceinline__ void align(const double* g, const double* ef, double omega, double* out) {
+    out[0] = out[1] = out[2] = 0.0;
+    const double gg = dot3_rn(g, g);
+    if (gg == 0.0) return;                       // |g| != 0 test of the reference (sqrt(x) == 0 only for x == 0)
+    const double est = dot3(g, ef) * rsqrt(gg);
+    const double margin = 1e-11 * (fabs(ef[0]) + fabs(ef[1]) + fabs(ef[2]) + fabs(omega));
+    double d = est;
+    if (!(fabs(fabs(est) - fabs(omega)) > margin)) {   // too close to call (or NaN): the reference's sequence
+      const double n = sqrt(gg);
+      const double u[3] = {g[0] / n, g[1] / n, g[2] / n};
+      d = dot3_rn(u, ef);
     }
-    if (nT != 0.0) {
-      const double u[3] = {G[2][0] / nT, G[2][1] / nT, G[2][2] / nT};
-      const double d = dot3_rn(u, ef);
-      if (d > +p.omega_T) { dir[3][0] = ef[0]; dir[3][1] = ef[1]; dir[3][2] = ef[2]; }
-      else if (d < -p.omega_T) { dir[3][0] = -ef[0]; dir[3][1] = -ef[1]; dir[3][2] = -ef[2]; }
-    }
+    if (d > +omega) { out[0] = ef[0]; out[1] = ef[1]; out[2] = ef[2]; }
+    else if (d < -omega) { out[0] = -ef[0]; out[1] = -ef[1]; out[2] = -ef[2]; }
   }
 
   // U[var] at the qp, A[] nodal aux at the qp (unused), Dg[dir] = dir . grad phi_i

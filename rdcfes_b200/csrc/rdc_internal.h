@@ -10,6 +10,7 @@
 
 #define RDC_MAX_NEN 8
 #define RDC_MAX_QP 8
+#define RDC_ASM_MAX_SPLIT 64   /* partial sums of split phase-2 blocks per assembly CTA (shared memory) */
 
 namespace rdc {
 
@@ -67,6 +68,10 @@ struct HostSetup {
   std::vector<int32_t> cta_node;                 // [ncta+1] node ranges of the assembly CTAs
   std::vector<int32_t> cptr;                     // [nnzb+1] into clist
   std::vector<uint16_t> clist;                   // j * pairs_per_cta + pair index inside the CTA
+  // phase-2 work list of the assembly kernel: a block's contributor run is cut into pieces of at most `chunk` entries so
+  // that the 24-contributor diagonal blocks do not hold up warps whose other lanes have ~6 (task = 2 x int32, see setup.cpp)
+  std::vector<int32_t> task;                     // [2 * ntask]
+  std::vector<int32_t> task_ptr;                 // [ncta+1]
   int pairs_per_cta = 0;
   // halo exchange (distributed): ghosts are ordered by owner rank, so each neighbour's ghosts are contiguous
   std::vector<int> nbr_rank;                     // neighbours
@@ -120,7 +125,7 @@ struct rdc_ctx {
   double* d_xyz = nullptr;           // [n_loc*4] padded (x,y,z,0): one 32-byte sector per node
   double* d_efield = nullptr;        // [E_loc*3]
   int32_t *d_n2e_ptr = nullptr, *d_pair = nullptr, *d_rowptr = nullptr, *d_col = nullptr, *d_diag_blk = nullptr;
-  int32_t *d_cta_node = nullptr, *d_cptr = nullptr;
+  int32_t *d_cta_node = nullptr, *d_task = nullptr;
   uint16_t* d_clist = nullptr;
   int32_t* d_dofmap = nullptr;       // [n_loc*nv] global dof id of each local dof (gather/scatter of user vectors)
   int ncta = 0;

@@ -238,6 +238,8 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
     S.rowptr[n + 1] = (int32_t)s;
   }
   const int64_t nnzb = S.rowptr[no];
+  for (int32_t n = 0; n < no; n++)
+    if (rowlen[n] > 255) { err = "a node has more than 255 neighbours"; return RDC_E_MESH; }
   S.col.resize((size_t)nnzb);
   S.diag_blk.resize((size_t)no);
 #pragma omp parallel
@@ -264,7 +266,7 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
   {
     int32_t start_pairs = 0;
     for (int32_t n = 0; n < no; n++) {
-      if (S.n2e_ptr[n + 1] - start_pairs > pairs_per_cta || n - S.cta_node.back() >= pairs_per_cta) {
+      if (S.n2e_ptr[n + 1] - start_pairs > pairs_per_cta || n - S.cta_node.back() >= std::min(pairs_per_cta, 255)) {
         S.cta_node.push_back(n);
         start_pairs = S.n2e_ptr[n];
       }
@@ -307,6 +309,61 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
         for (int j = 0; j < nen; j++) {
           const int32_t k = (int32_t)(std::lower_bound(rc0, rc0 + len, S.conn[le * nen + j]) - rc0);
           S.clist[(size_t)cur[k]++] = (uint16_t)(j * pairs_per_cta + (p - pair0));
+        }
+      }
+    }
+  }
+
+  // phase-2 tasks.  Task = {x, y}: x = row inside the CTA | block inside the row << 8 | first contributor (relative to the
+  // CTA's contributor base) << 16 ; y = number of contributors | piece index << 8 | pieces of this block << 16 | slot of the
+  // piece's partial sum << 24 (split blocks only).  Pieces of one block are consecutive tasks.  At most MAX_SPLIT pieces of
+  // split blocks per CTA (the partial sums live in shared memory): the piece length doubles from 8 until that holds.
+  {
+    const int MAX_SPLIT = RDC_ASM_MAX_SPLIT;
+    S.task_ptr.assign((size_t)ncta + 1, 0);
+    std::vector<uint8_t> chunk_of((size_t)ncta, 8);
+    bool bad = false;
+#pragma omp parallel for schedule(static)
+    for (int32_t cta = 0; cta < ncta; cta++) {
+      const int32_t b0 = S.rowptr[S.cta_node[cta]], b1 = S.rowptr[S.cta_node[cta + 1]];
+      int ch = 8, ntask = 0;
+      for (;; ch *= 2) {
+        int nsplit = 0;
+        ntask = 0;
+        for (int32_t B = b0; B < b1; B++) {
+          const int cnt = S.cptr[(size_t)B + 1] - S.cptr[B];
+          const int np = cnt > ch ? (cnt + ch - 1) / ch : 1;
+          ntask += np;
+          if (np > 1) nsplit += np;
+        }
+        if (nsplit <= MAX_SPLIT || ch >= 128) { if (nsplit > MAX_SPLIT) bad = true; break; }
+      }
+      chunk_of[cta] = (uint8_t)ch;
+      S.task_ptr[(size_t)cta + 1] = ntask;
+    }
+    if (bad) { err = "assembly CTA with too many long contributor lists"; return RDC_E_MESH; }
+    for (int32_t cta = 0; cta < ncta; cta++) {
+      const int64_t s = (int64_t)S.task_ptr[cta] + S.task_ptr[(size_t)cta + 1];
+      if (s > 0x3fffffff) { err = "too many assembly tasks for 32-bit offsets"; return RDC_E_ARG; }
+      S.task_ptr[(size_t)cta + 1] = (int32_t)s;
+    }
+    S.task.assign((size_t)S.task_ptr[ncta] * 2, 0);
+#pragma omp parallel for schedule(static)
+    for (int32_t cta = 0; cta < ncta; cta++) {
+      const int ch = chunk_of[cta];
+      const int32_t cbase = S.cptr[S.rowptr[S.cta_node[cta]]];
+      int32_t* out = S.task.data() + (size_t)S.task_ptr[cta] * 2;
+      int slot = 0;
+      for (int32_t n = S.cta_node[cta]; n < S.cta_node[cta + 1]; n++) {
+        const int32_t r0 = S.rowptr[n], L = S.rowptr[n + 1] - r0;
+        for (int32_t kk = 0; kk < L; kk++) {
+          const int32_t c0 = S.cptr[(size_t)r0 + kk], cnt = S.cptr[(size_t)r0 + kk + 1] - c0;
+          const int np = cnt > ch ? (cnt + ch - 1) / ch : 1;
+          for (int k = 0; k < np; k++) {
+            const int start = c0 - cbase + k * ch, len = std::min(ch, cnt - k * ch);
+            *out++ = (n - S.cta_node[cta]) | (kk << 8) | (start << 16);
+            *out++ = len | (k << 8) | (np << 16) | ((np > 1 ? slot++ : 0) << 24);
+          }
         }
       }
     }

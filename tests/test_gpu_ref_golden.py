@@ -46,9 +46,10 @@ def test_gpu_matches_reference_vectors(model, tag, ksp):
             assert np.linalg.norm(u1 - g["u1"]) <= 1e-8 * np.linalg.norm(g["u1"])
     uN = gpu.get_solution()
     nv = cases.P.NVARS[model]
-    for a in range(nv):   # every species separately
+    for a in range(nv):   # every species separately; a species that is numerically absent (PIHNA's n stays ~1e-15 next
+        # to cell densities of 1e4) is held to 1e-6 of 1e-12 x the state's norm instead of its own round-off-sized norm
         ra, ga = uN.reshape(-1, nv)[:, a], g["uN"].reshape(-1, nv)[:, a]
-        assert np.linalg.norm(ra - ga) <= 1e-6 * max(np.linalg.norm(ga), 1e-300)
+        assert np.linalg.norm(ra - ga) <= 1e-6 * max(np.linalg.norm(ga), 1e-12 * np.linalg.norm(g["uN"]))
     assert np.linalg.norm(uN - g["uN"]) <= 1e-8 * np.linalg.norm(g["uN"])
     if model == cases.RIPF:
         assert gpu.stats().ripf_rt_total_max == int(g["rt_max"])
