@@ -65,6 +65,18 @@ struct Pulse { double cM, c0, c1; };
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
+// x^e and x^(e-1) for the capacity laws Tau = (1 - T/kappa)^e (pihna.C:444-472, coupled_hcc.C:510-532).
+// The shipped configurations use e = 3 (run/PIHNA/input.dat:26, run/Coupled/HCC/input.dat:30); small integer exponents
+// are formed by multiplication (within 2 ulp of pow, against a 1e-12 tolerance), anything else by pow -- the branch
+// is uniform over the grid.  The generic pow costs more than the rest of the quadrature point.
+__device__ __forceinline__ void pow_pair(double x, double e, double& xe, double& xe1) {
+  if (e == 1.0) { xe1 = 1.0; xe = x; }
+  else if (e == 2.0) { xe1 = x; xe = x * x; }
+  else if (e == 3.0) { xe1 = x * x; xe = xe1 * x; }
+  else if (e == 4.0) { const double x2 = x * x; xe1 = x2 * x; xe = x2 * x2; }
+  else { xe = pow(x, e); xe1 = pow(x, e - 1.0); }
+}
+
 template <int NV>
 struct Coef {
   double F0[NV], F1[NV];
@@ -206,7 +218,7 @@ struct Pihna {
       const double Te = (n + c + hh + v) / p.Kappa_k;
       if (Te <= 0.0) { Tau = 1.0; dT = 0.0; }
       else if (Te >= 1.0) { Tau = 0.0; dT = 0.0; }
-      else { Tau = pow(1.0 - Te, p.ek); dT = (-p.ek / p.Kappa_k) * pow(1.0 - Te, p.ek - 1.0); }
+      else { double xe1; pow_pair(1.0 - Te, p.ek, Tau, xe1); dT = (-p.ek / p.Kappa_k) * xe1; }
     }
     // pihna.C:474-499 (0/0 = NaN fails both comparisons like on the host)
     double Ve, dVc, dVv;
@@ -336,7 +348,7 @@ struct Ripf {
     const double VF_total = p.VF_s + p.VF_p + (cc + fb);
     double Tau = 0.0, dT = 0.0;
     if (VF_total < 1.0) {
-      Tau = pow(1.0 - VF_total, p.VF_e);
+      Tau = pow(1.0 - VF_total, p.VF_e);   // feeds the comparison below: kept as the reference computes it
       dT = -p.VF_e * pow(1.0 - VF_total, p.VF_e - 1.0);
       if (Tau < p.VF_min) { Tau = 0.0; dT = 0.0; }
     }
@@ -520,7 +532,7 @@ struct Hcc {
       const double Te = (l + c + n) / p.Kappa_k;
       if (Te <= 0.0) { Tau = 1.0; dT = 0.0; }
       else if (Te >= 1.0) { Tau = 0.0; dT = 0.0; }
-      else { Tau = pow(1.0 - Te, p.ek); dT = (-p.ek / p.Kappa_k) * pow(1.0 - Te, p.ek - 1.0); }
+      else { double xe1; pow_pair(1.0 - Te, p.ek, Tau, xe1); dT = (-p.ek / p.Kappa_k) * xe1; }
     }
     const double dif = c > p.Lambda_k ? p.diffuse_c : 0.0;  // coupled_hcc.C:534
     const double h = p.dt2;
