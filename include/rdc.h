@@ -227,6 +227,9 @@ int rdc_region_last_mean(rdc_ctx*, int var, double* mean /* [n_regions] */);
 /* read-only streaming probe over the stored operator values (reference point for the SpMV roofline): mean ms, bytes */
 int rdc_bench_stream(rdc_ctx*, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes);
 
+/* cost of one grid barrier (mode 0) / reduction-barrier (mode 1) of the persistent Krylov kernel on this device: mean us */
+int rdc_bench_barrier(rdc_ctx*, int reps, int ctas_per_sm, int mode, double* mean_us);
+
 /* ---- parity / introspection ------------------------------------------------------------------- */
 /* Scalar CSR in global dof numbering, rows and columns sorted: exactly the (node graph + I) (x) dense
  * v x v pattern libMesh preallocates.  Buffers are malloc'ed by the library; free
@@ -270,7 +273,8 @@ int rdc_probe_partition(int elem_type, int nvars, int64_t n_nodes, int64_t n_ele
                         int32_t** send_ptr, int32_t** send_glob, int32_t** recv_ptr, int32_t** recv_glob);
 /* Tuning switch of the context (defaults: environment RDC_<NAME>): "spmv_tma" 1/0 (TMA-staged or LDG SpMV),
  * "spmv_minb", "spmv_ctas_per_sm", "tma_ctas_per_sm", "tma_stages", "sync_every", "p2p_fused_ar",
- * "p2p_fused_halo", "trace".  Results do not depend on them beyond floating-point summation order. */
+ * "p2p_fused_halo", "bicg_persist" 1/0 (BiCGStab as one cooperative launch with grid barriers, or five launches per
+ * iteration), "trace".  Results do not depend on them beyond floating-point summation order. */
 int rdc_set_option(rdc_ctx*, const char* name, int value);
 /* Host-only probes of set-up logic, for CPU tests (arrays malloc'ed by the library, rdc_free): the SpMV tile cutter
  * (tiles = n_tiles x {row0, nrows, first block, nblocks}; n_tiles = -1 when a row exceeds max_blocks) and the region

@@ -24,7 +24,7 @@ static const OptName kOptions[] = {
     {"spmv_ctas_per_sm", &rdc_options::spmv_ctas_per_sm}, {"tma_ctas_per_sm", &rdc_options::tma_ctas_per_sm},
     {"tma_stages", &rdc_options::tma_stages}, {"sync_every", &rdc_options::sync_every},
     {"p2p_fused_ar", &rdc_options::p2p_fused_ar}, {"p2p_fused_halo", &rdc_options::p2p_fused_halo},
-    {"trace", &rdc_options::trace}};
+    {"bicg_persist", &rdc_options::bicg_persist}, {"trace", &rdc_options::trace}};
 
 static void options_from_env(rdc_options& o) {
   for (const OptName& k : kOptions) {
@@ -602,6 +602,20 @@ extern "C" int rdc_bench_stream(rdc_ctx* c, int reps, int ctas_per_sm, double* m
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   *mean_ms = ms / reps;
   if (bytes) *bytes = (int64_t)((size_t)c->nnzb * c->nkv / 2 * 16);
+  return rc;
+}
+
+extern "C" int rdc_bench_barrier(rdc_ctx* c, int reps, int ctas_per_sm, int mode, double* mean_us) {
+  CHECK_CTX(c);
+  if (reps < 1 || !mean_us || ctas_per_sm < 1 || ctas_per_sm > 8) return RDC_E_ARG;
+  int rc = launch_barrier_probe(c, 10, ctas_per_sm, mode);  // warm-up
+  cudaEventRecord(c->ev0, c->stream);
+  if (!rc) rc = launch_barrier_probe(c, reps, ctas_per_sm, mode);
+  cudaEventRecord(c->ev1, c->stream);
+  cudaEventSynchronize(c->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  *mean_us = 1e3 * ms / reps;
   return rc;
 }
 

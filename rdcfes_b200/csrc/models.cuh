@@ -227,10 +227,11 @@ struct Pihna {
       const double Ve_ = v / chv;
       if (Ve_ <= 0.0) { Ve = 0.0; dVc = 0.0; dVv = 0.0; }
       else if (Ve_ >= 1.0) { Ve = 1.0; dVc = 0.0; dVv = 0.0; }
-      else { Ve = Ve_; dVc = -Ve_ / chv; dVv = (1.0 - Ve_) / chv; }
+      else { const double rc = 1.0 / chv; Ve = Ve_; dVc = -Ve_ * rc; dVv = (1.0 - Ve_) * rc; }   // one reciprocal for both derivatives
     }
     const double dVh = dVc;
-    const double Ua = a / (a + p.Kappa_a), dUa = 1.0 / (a + p.Kappa_a) - Ua / (a + p.Kappa_a);  // pihna.C:501-502
+    const double ra = 1.0 / (a + p.Kappa_a);
+    const double Ua = a * ra, dUa = ra - Ua * ra;  // pihna.C:501-502 (a/(a+K), 1/(a+K) - Ua/(a+K)) from one reciprocal
     const double dif_c = c > p.Lambda_k ? p.dif_c : 0.0, tax_c = c > p.Lambda_k ? p.tax_c : 0.0;  // pihna.C:504-509
     const double dif_h = hh > p.Lambda_k ? p.dif_h : 0.0, tax_h = hh > p.Lambda_k ? p.tax_h : 0.0;
     const double dif_v = v > p.Lambda_k ? p.dif_v : 0.0, tax_v = v > p.Lambda_k ? p.tax_v : 0.0;

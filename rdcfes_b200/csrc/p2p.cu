@@ -96,6 +96,27 @@ void p2p_fill_halo_args(rdc_ctx* c, HaloArgs* A, int* max_blk, int* total_blk, u
   *total_blk = A->blk_ptr[nn];
 }
 
+// the same description for a given parity, without consuming a sequence number (persistent solver: the kernel counts)
+void p2p_fill_halo_args_parity(rdc_ctx* c, HaloArgs* A, int par) {
+  P2P* P = c->p2p;
+  const int nn = (int)c->S.nbr_rank.size();
+  A->n_nbr = nn;
+  A->n_owned = c->S.n_owned;
+  A->blk_ptr[0] = 0;
+  A->src = (const ulonglong2*)(P->arena + P->stage_off[par]);
+  for (int k = 0; k < nn; k++) {
+    const int q = c->S.nbr_rank[k];
+    A->dst[k] = (ulonglong2*)((unsigned char*)P->peer[q] + P->stage_off[par]) + (size_t)P->dst_node_off[k] * c->nv;
+    A->send_ptr[k] = c->S.send_ptr[k];
+    A->recv_ptr[k] = c->S.recv_ptr[k];
+    const int cnt = std::max(c->S.send_ptr[k + 1] - c->S.send_ptr[k], c->S.recv_ptr[k + 1] - c->S.recv_ptr[k]) * c->nv;
+    A->nblk[k] = std::max(1, std::min(HALO_MAX_BLK, (cnt + 255) / 256));
+    A->blk_ptr[k + 1] = A->blk_ptr[k] + A->nblk[k];
+  }
+  A->send_ptr[nn] = c->S.send_ptr[nn];
+  A->recv_ptr[nn] = c->S.recv_ptr[nn];
+}
+
 int p2p_launch_halo(rdc_ctx* c, double* x, bool check_done) {
   P2P* P = c->p2p;
   const int nn = (int)c->S.nbr_rank.size();

@@ -104,6 +104,7 @@ struct rdc_options {
   int sync_every = 0;          // iterations queued ahead of the convergence flag (0 = default)
   int p2p_fused_ar = 1;        // all-reduce finished inside the producing kernel
   int p2p_fused_halo = 1;      // ghost exchange inside the BiCGStab vector kernels
+  int bicg_persist = 1;        // BiCGStab as one cooperative launch (solver.cu k_bicgstab_persist); 0 = five launches per iteration
   int trace = 0;               // print the device time of every operation of BiCGStab iteration 4
 };
 
@@ -181,6 +182,7 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
 int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done = false);
 int launch_clamp(rdc_ctx* c);
 int launch_stream_probe(rdc_ctx* c, int ctas_per_sm);
+int launch_barrier_probe(rdc_ctx* c, int reps, int ctas_per_sm, int mode);
 int spmv_masks_ok();                // solver.cu's entry masks agree with the model definitions
 int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc);     // dst_loc[l] = src[dofmap[l]]
 int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob);    // owned part only

@@ -56,6 +56,11 @@ struct SolverWork {
   int* h_ring = nullptr;     // pinned copies of the convergence flag
   int4* tiles = nullptr;     // SpMV tiles {row0, nrows, first block, nblocks} (k_spmv_tma)
   int n_tiles = 0;
+  unsigned* flag = nullptr;             // epoch flag of the persistent solver's grid barriers
+  unsigned long long* t_spmv = nullptr; // [8] phase timers of the last persistent solve (see PersistArgs)
+  double persist_phase_ms[4] = {0, 0, 0, 0};
+  int persist_grid = 0;                 // co-resident CTAs of k_bicgstab_persist on this device (0: not queried yet)
+  unsigned long long n_persist = 0;     // persistent solves so far (parity selects the epoch flag)
 };
 
 namespace rdc {
@@ -908,6 +913,9 @@ int solver_init(rdc_ctx* c) {
       W->n_tiles = (int)(tl.size() / 4);
     }
   }
+  RDC_CUDA(cudaMalloc(&W->flag, 2 * sizeof(unsigned)));
+  RDC_CUDA(cudaMemsetAsync(W->flag, 0, 2 * sizeof(unsigned), c->stream));
+  RDC_CUDA(cudaMalloc(&W->t_spmv, 8 * sizeof(unsigned long long)));
   RDC_CUDA(cudaHostAlloc(&W->h_ring, sizeof(int) * SolverWork::RING, cudaHostAllocMapped));
   memset(W->h_ring, 0, sizeof(int) * SolverWork::RING);
   return 0;
@@ -957,7 +965,7 @@ void solver_free(rdc_ctx* c) {
   cudaFreeHost(W->h_scal); cudaFreeHost(W->h_state);
   for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) cudaEventDestroy(W->ev[k]);
   cudaFreeHost(W->h_ring);
-  cudaFree(W->tiles);
+  cudaFree(W->tiles); cudaFree(W->flag); cudaFree(W->t_spmv);
   delete W;
   c->work = nullptr;
 }
@@ -1005,7 +1013,7 @@ static int gs_update(rdc_ctx* c, int nvec, const double* V, double* w, const dou
 
 static int poll(rdc_ctx* c) {
   SolverWork* W = c->work;
-  RDC_CUDA(cudaMemcpyAsync(W->h_state, W->state, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
+  RDC_CUDA(cudaMemcpyAsync(W->h_state, W->state, sizeof(int) * 8, cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaMemcpyAsync(W->h_scal, W->scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
   return p2p_check_error(c);   // a timed-out peer exchange surfaces at every host synchronisation of every solver
@@ -1412,6 +1420,530 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
   return 0;
 }
 
+
+// ============================================================================================================
+// Persistent BiCGStab: the whole solve is ONE cooperative launch.
+//
+// The five-launch iteration above pays, per kernel, the launch, the ramp of 888 CTAs and the tail of the slowest one
+// (~10 us each at 1.3 M tets per GPU -- a third of the iteration at 8 GPUs, 12 % at one GPU).  Here a resident grid
+// (the TMA SpMV's own: 148 x CTAs/SM, operator tiles dealt round-robin) walks through the phases of every iteration
+//   P: p = r + beta (p - omega v) [+ghosts] | S1: v = B A p, <r0,v> | S: s = r - alpha v [+ghosts] |
+//   S2: t = B A s, <s,t>, <t,t> | XR: x += alpha p + omega s, r = s - omega t, <r0,r>, <r,r>
+// separated by grid barriers.  The three reductions ARE barriers: every CTA adds its partial sums to a list, the last
+// one to arrive adds the list in a fixed order (and, distributed, finishes the sum across the ranks over NVLink peer
+// memory with the tag-in-word slots), publishes the result and releases the epoch flag all CTAs spin on.  Scalars
+// (alpha, omega, beta) and the convergence decision are derived by every thread from the same published sums, so all
+// CTAs -- and all ranks -- leave the loop in the same iteration without any host involvement.
+// Coherence: vectors written in one phase are read in the next by other CTAs; the barrier's release/acquire pair plus a
+// gpu-scope fence in every thread (which drops the SM's L1 lines) makes the plain, L1-cached loads of the next phase see
+// them -- the x gather of the SpMV keeps its L1 reuse inside a phase.
+// Same arithmetic, same summation orders as the five-launch version: the two produce bit-identical iterates (tested).
+struct PersistHalo {
+  HaloArgs A[2];                 // by parity of the exchange sequence number (staging areas are double-buffered)
+  const int32_t* send_idx = nullptr;
+  P2PHeader* hdr = nullptr;
+  unsigned long long seq0 = 0;   // exchanges done before this solve
+  int on = 0, nv = 1;
+};
+struct PersistArgs {
+  int n_tiles; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val;
+  const double* scale; const double* b;
+  size_t n;
+  double *x, *r, *r0, *v, *s, *t, *p0, *p1;
+  double* partial; unsigned* counter; unsigned* flag; unsigned* flag_other; double* D; double* S; int* state;
+  double rtol; int maxits;
+  ArCtx ar;            // ar.seq = all-reduces done before this solve
+  PersistHalo halo;
+  unsigned long long* t_spmv;   // [8] globaltimer ns of block 0: [0] SpMV phases, [1] their number, [2] P, [3] S, [4] XR phases (each with its barrier), [5] set-up
+};
+
+// arrive at barrier `epoch` (1, 2, ...) and wait for it.  Release: every thread's writes -> __syncthreads -> thread 0
+// fence + atomic; acquire: thread 0 spins on the flag and fences (L1 invalidation), __syncthreads.
+__device__ __forceinline__ void grid_wait(unsigned* flag, unsigned epoch) {
+  if (threadIdx.x == 0) {
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); } while (v < epoch);
+    __threadfence();   // one gpu-scope fence per CTA: orders the CTA behind the release and drops the SM's stale L1 lines
+  }
+  __syncthreads();     // the other threads are ordered behind thread 0's acquire by the CTA barrier (cumulativity)
+}
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned* flag, unsigned epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+      *counter = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    }
+  }
+  grid_wait(flag, epoch);
+}
+// reduction + barrier: out[k] = sum over all threads of the grid (and all ranks) of v[k], k < nval <= 2
+__device__ __forceinline__ void grid_reduce_barrier(double (&v)[2], int nval, double* partial, unsigned* counter, unsigned* flag,
+                                                    unsigned epoch, double* out, const ArCtx& ar) {
+  __shared__ double s_red[RED_THREADS / 32][2];
+  __shared__ double s_tot[2];
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const double w = warp_sum(v[k]);
+    if (lane == 0) s_red[wid][k] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && threadIdx.x < nval) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < RED_THREADS / 32; w++) s += s_red[w][threadIdx.x];
+    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+    __threadfence();   // the two writers publish their partial sums ...
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); s_last = (atomicAdd(counter, 1u) == gridDim.x - 1); }   // ... and the CTA's vector writes
+  __syncthreads();
+  if (s_last) {   // same order of additions as grid_reduce: thread t takes blocks t, t+256, ..., then the fixed tree --
+    // but both values in one pass and all loads of a thread in flight together (the partial list sits in L2: four
+    // dependent round trips per value were 3 us of a 7.7 us reduction-barrier)
+    __threadfence();
+    constexpr int NB = (SPMV_MAX_GRID + RED_THREADS - 1) / RED_THREADS;
+    double pv[2][NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const unsigned b = threadIdx.x + (unsigned)j * RED_THREADS;
+#pragma unroll
+      for (int k = 0; k < 2; k++) pv[k][j] = (b < gridDim.x && k < nval) ? __ldcg(partial + (size_t)k * gridDim.x + b) : 0.0;
+    }
+    double sk[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+#pragma unroll
+      for (int j = 0; j < NB; j++)
+        if (threadIdx.x + (unsigned)j * RED_THREADS < gridDim.x) sk[k] += pv[k][j];
+      sk[k] = warp_sum(sk[k]);
+    }
+    __syncthreads();
+    if (lane == 0) { s_red[wid][0] = sk[0]; s_red[wid][1] = sk[1]; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < RED_THREADS / 32; w++) t += s_red[w][threadIdx.x];
+      s_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (ar.nranks > 1) {
+      const int par = (int)(ar.seq & 1ull);
+      const unsigned tag = (unsigned)ar.seq;
+      const int q = threadIdx.x / 2, k = threadIdx.x % 2;
+      double got = 0.0;
+      if (q < ar.nranks && k < nval) {
+        ll_store(&ar.peer[q]->ll[par][ar.me][k][0], s_tot[k], tag);
+        const unsigned long long t0 = global_ns();
+        int spins = 0;
+        while (!ll_load(&ar.mine->ll[par][q][k][0], tag, &got)) {
+          if ((++spins & 1023) == 0 && global_ns() - t0 > P2P_TIMEOUT_NS) { ar.mine->error = 1; break; }
+        }
+      }
+      __syncthreads();
+      __shared__ double s_in[RDC_MAX_RANKS][2];
+      if (q < ar.nranks && k < nval) s_in[q][k] = got;
+      __syncthreads();
+      if (threadIdx.x < 2 && threadIdx.x < nval) {
+        double t = 0.0;
+        for (int r = 0; r < ar.nranks; r++) t += s_in[r][threadIdx.x];
+        out[threadIdx.x] = t;
+      }
+    } else if (threadIdx.x < 2 && threadIdx.x < nval) {
+      out[threadIdx.x] = s_tot[threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      *counter = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    }
+  }
+  grid_wait(flag, epoch);
+}
+
+// one SpMV phase of the persistent kernel: the tile loop of k_spmv_tma with a tile counter `gi` that keeps running over
+// the phases (stage index and mbarrier parity follow it)
+template <int NV, unsigned KMASK, int MODE>
+__device__ __forceinline__ void persist_spmv(const PersistArgs& A, const double* __restrict__ x, double* __restrict__ y,
+                                             const double* __restrict__ w, double* __restrict__ y2, unsigned char* s_raw,
+                                             unsigned long long* s_bar, unsigned& gi, double (&d)[2]) {
+  constexpr int G = 16, STAGES = 2;
+  constexpr int NKV = popc_c(KMASK);
+  typedef SpmvStage<NKV> ST;
+  const int tid = threadIdx.x, lane = tid & (G - 1), hw = tid / G;
+  const unsigned hmask = 0xffffu << (tid & 16);
+  const int4* __restrict__ tiles = A.tiles;
+  const int n_tiles = A.n_tiles;
+  auto issue = [&](int tile, unsigned slot) {
+    const int4 t = tiles[tile];
+    const int skip_v = (int)(((long long)t.z * NKV) & 1), skip_c = t.z & 3, skip_r = t.x & 3;
+    const unsigned vb = (unsigned)(((skip_v + t.w * NKV) * 8 + 15) & ~15);
+    const unsigned cb = (unsigned)(((skip_c + t.w) * 4 + 15) & ~15);
+    const unsigned rb = (unsigned)(((skip_r + t.y + 1) * 4 + 15) & ~15);
+    unsigned char* base = s_raw + (size_t)(slot % STAGES) * ST::BYTES;
+    const unsigned bar = smem_u32(&s_bar[slot % STAGES]);
+    mbar_expect_tx(bar, vb + cb + rb);
+    bulk_g2s(smem_u32(base), A.val + ((long long)t.z * NKV - skip_v), vb, bar);
+    bulk_g2s(smem_u32(base + ST::VAL_BYTES), A.col + (t.z - skip_c), cb, bar);
+    bulk_g2s(smem_u32(base + ST::VAL_BYTES + ST::COL_BYTES), A.rowptr + (t.x - skip_r), rb, bar);
+  };
+  const int first = (int)blockIdx.x, tstride = (int)gridDim.x;
+  if (tid == 0 && first < n_tiles) issue(first, gi);
+  int4 tn = first < n_tiles ? tiles[first] : make_int4(0, 0, 0, 0);
+#pragma unroll 1
+  for (int tile = first; tile < n_tiles; tile += tstride, gi++) {
+    const unsigned stage = gi % STAGES;
+    const int4 t = tn;
+    if (tile + tstride < n_tiles) tn = tiles[tile + tstride];
+    if (tid == 0 && tile + tstride < n_tiles) issue(tile + tstride, gi + 1);
+    const bool live = hw < t.y;
+    const int row = t.x + hw;
+    const size_t o = (size_t)row * NV + (lane < NV ? lane : 0);
+    double sc = 1.0, wv = 0.0;
+    if (live && lane < NV) {
+      if (A.scale) sc = A.scale[o];
+      if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
+      if (MODE == SPMV_DOT_SELF) wv = x[o];
+    }
+    mbar_wait(smem_u32(&s_bar[stage]), (unsigned)((gi / STAGES) & 1u));
+    if (live) {
+      const unsigned char* base = s_raw + (size_t)stage * ST::BYTES;
+      const double* s_val = reinterpret_cast<const double*>(base) + (((long long)t.z * NKV) & 1);
+      const int* s_col = reinterpret_cast<const int*>(base + ST::VAL_BYTES) + (t.z & 3);
+      const int* s_rp = reinterpret_cast<const int*>(base + ST::VAL_BYTES + ST::COL_BYTES) + (t.x & 3);
+      const int r0 = s_rp[hw] - t.z;
+      const int L = s_rp[hw + 1] - s_rp[hw];
+      double acc[NV];
+#pragma unroll
+      for (int a = 0; a < NV; a++) acc[a] = 0.0;
+#pragma unroll 1
+      for (int k = lane; k < L; k += G) {
+        const int c = s_col[r0 + k];
+        double xv[NV];
+#pragma unroll
+        for (int b = 0; b < NV; b++) xv[b] = x[(size_t)c * NV + b];
+        const double* v0 = s_val + (size_t)r0 * NKV + k;
+#pragma unroll
+        for (int ab = 0; ab < NV * NV; ab++)
+          if (KMASK >> ab & 1u) acc[ab / NV] = fma(v0[slot_c(KMASK, ab) * L], xv[ab % NV], acc[ab / NV]);
+      }
+#pragma unroll
+      for (int off = G / 2; off > 0; off >>= 1)
+#pragma unroll
+        for (int a = 0; a < NV; a++) acc[a] += __shfl_xor_sync(hmask, acc[a], off, G);
+      if (lane < NV) {
+        double mine = acc[0];
+#pragma unroll
+        for (int a = 1; a < NV; a++)
+          if (lane == a) mine = acc[a];
+        if (MODE == SPMV_DOT_W) {
+          const double yv = mine * sc;
+          y[o] = yv;
+          d[0] = fma(wv, yv, d[0]);
+        } else if (MODE == SPMV_DOT_SELF) {
+          const double yv = mine * sc;
+          y[o] = yv;
+          d[0] = fma(wv, yv, d[0]);
+          d[1] = fma(yv, yv, d[1]);
+        } else {
+          const double yv = (wv - mine) * sc;
+          y[o] = yv;
+          if (y2) y2[o] = yv;
+          d[0] = fma(yv, yv, d[0]);
+          d[1] = fma(wv * sc, wv * sc, d[1]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ghost exchange of a vector inside a phase: virtual exchange blocks are dealt to the CTAs round-robin; all sends of a
+// CTA go out before it polls, so no CTA ever waits for a peer before the peer's data can be on its way
+template <class F>
+__device__ __forceinline__ void persist_halo_send(const PersistHalo& H, int par, unsigned long long seq, F val) {
+  const HaloArgs& A = H.A[par];
+  const unsigned tag = (unsigned)seq;
+  const int total = A.blk_ptr[A.n_nbr];
+  for (int vb = (int)blockIdx.x; vb < total; vb += (int)gridDim.x) {
+    int k = 0;
+    while (vb >= A.blk_ptr[k + 1]) k++;
+    const int nb = A.nblk[k], b = vb - A.blk_ptr[k];
+    const int s0 = A.send_ptr[k], scnt = (A.send_ptr[k + 1] - s0) * H.nv;
+    ulonglong2* dst = A.dst[k];
+    for (int i = b * blockDim.x + threadIdx.x; i < scnt; i += nb * blockDim.x) {
+      const int node = i / H.nv, a = i - node * H.nv;
+      tag_store(dst + i, val((size_t)H.send_idx[s0 + node] * H.nv + a), tag);
+    }
+  }
+}
+__device__ __forceinline__ void persist_halo_recv(const PersistHalo& H, int par, unsigned long long seq, double* __restrict__ x) {
+  const HaloArgs& A = H.A[par];
+  const unsigned tag = (unsigned)seq;
+  const int total = A.blk_ptr[A.n_nbr];
+  for (int vb = (int)blockIdx.x; vb < total; vb += (int)gridDim.x) {
+    int k = 0;
+    while (vb >= A.blk_ptr[k + 1]) k++;
+    const int nb = A.nblk[k], b = vb - A.blk_ptr[k];
+    const int r0 = A.recv_ptr[k] * H.nv, rcnt = (A.recv_ptr[k + 1] - A.recv_ptr[k]) * H.nv;
+    const ulonglong2* src = A.src + r0;
+    double* ghost = x + (size_t)A.n_owned * H.nv + r0;
+    for (int i = b * blockDim.x + threadIdx.x; i < rcnt; i += nb * blockDim.x) {
+      double v = 0.0;
+      const unsigned long long t0 = global_ns();
+      int spins = 0;
+      bool got;
+      while (!(got = tag_load(src + i, tag, &v))) {
+        if ((++spins & 1023) == 0 && global_ns() - t0 > P2P_TIMEOUT_NS) { H.hdr->error = 1; break; }
+      }
+      if (got) ghost[i] = v;
+    }
+  }
+}
+
+template <int NV, unsigned KMASK>
+__global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_persist(const PersistArgs A) {
+  constexpr int STAGES = 2;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ __align__(8) unsigned long long s_bar[STAGES];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(smem_u32(&s_bar[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // the epoch flag of the NEXT solve is cleared here (every CTA of the previous solve left its last barrier long ago);
+  // this solve's flag was cleared by the previous one (both start at zero): no memset between the solves
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *A.flag_other = 0u; A.state[0] = 0; A.state[3] = 0; }
+  unsigned epoch = 0, gi = 0;
+  unsigned long long nar = 0, nhalo = 0;          // reductions / exchanges of this solve so far
+  unsigned long long t_acc = 0, t_cnt = 0, t_p = 0, t_s = 0, t_xr = 0, t_mark = 0;
+  const size_t n = A.n;
+  const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  double* const D = A.D;                 // written by the last block of a reduction: read it from L2, never from a stale L1 line
+  auto Dl = [&](int k) { return __ldcg(D + k); };
+  auto ar_next = [&]() { ArCtx a = A.ar; a.seq = A.ar.seq + (++nar); return a; };
+  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+
+  // r = r0 = B (b - A x), <r,r>, ||B b||^2 (the ghosts of x were exchanged by the host-side launch before)
+  {
+    double d[2] = {0.0, 0.0};
+    persist_spmv<NV, KMASK, SPMV_RESID>(A, A.x, A.r, A.b, A.r0, s_raw, s_bar, gi, d);
+    grid_reduce_barrier(d, 2, A.partial, A.counter, A.flag, ++epoch, D + D_INIT, ar_next());
+  }
+  int it = 0;
+  for (;; it++) {
+    const int rn = it == 0 ? D_INIT : D_XR0 + 2 * ((it - 1) & 1);
+    const int ro = it <= 1 ? D_INIT : D_XR0 + 2 * ((it - 2) & 1);
+    const double rho = Dl(rn), rr = Dl(rn + (it == 0 ? 0 : 1));
+    const double bnorm = sqrt(Dl(D_INIT + 1));
+    const double res = sqrt(rr), target = fmax(A.rtol * bnorm, 1e-50);
+    double beta = 0.0, omega = 0.0;
+    int stop = 0, bad = 0;
+    if (!(res == res)) { stop = 1; bad = 1; }
+    else if (res <= target) stop = 1;
+    else if (it > 0) {
+      const double rho_old = Dl(ro);
+      const double alpha = rho_old / Dl(D_R0V);
+      omega = Dl(D_TT) != 0.0 ? Dl(D_TS) / Dl(D_TT) : 0.0;
+      if (omega == 0.0 || rho == 0.0) { stop = 1; bad = 1; }
+      beta = (rho / rho_old) * (alpha / omega);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      A.S[S_RES] = res; A.S[S_TARGET] = target; A.S[S_BNORM] = bnorm;
+      A.state[1] = it;
+      if (stop) { A.state[3] = bad; A.state[0] = 1; }
+    }
+    if (stop || it >= A.maxits) break;      // same published sums on every CTA and every rank: everybody leaves together
+    double* p = (it & 1) ? A.p1 : A.p0;
+    const double* p_old = (it & 1) ? A.p0 : A.p1;
+    // ---- P
+    if (timer) t_mark = global_ns();
+    {
+      const double* __restrict__ r = A.r;
+      const double* __restrict__ v = A.v;
+      const double* __restrict__ po = p_old;
+      double* __restrict__ pn = p;
+      auto pval = [=](size_t j) { return it == 0 ? r[j] : fma(beta, fma(-omega, v[j], po[j]), r[j]); };
+      unsigned long long hs = 0;
+      if (A.halo.on) { hs = A.halo.seq0 + (++nhalo); persist_halo_send(A.halo, (int)(hs & 1ull), hs, pval); }
+      if (it == 0) {
+#pragma unroll 4
+        for (size_t i = first; i < n; i += step) pn[i] = r[i];
+      } else {
+#pragma unroll 4
+        for (size_t i = first; i < n; i += step) pn[i] = fma(beta, fma(-omega, v[i], po[i]), r[i]);
+      }
+      if (A.halo.on) persist_halo_recv(A.halo, (int)(hs & 1ull), hs, p);
+    }
+    grid_barrier(A.counter, A.flag, ++epoch);
+    if (timer) t_p += global_ns() - t_mark;
+    // ---- S1: v = B A p, <r0, v>
+    {
+      unsigned long long t0 = 0;
+      if (timer) t0 = global_ns();
+      double d[2] = {0.0, 0.0};
+      persist_spmv<NV, KMASK, SPMV_DOT_W>(A, p, A.v, A.r0, nullptr, s_raw, s_bar, gi, d);
+      grid_reduce_barrier(d, 1, A.partial, A.counter, A.flag, ++epoch, D + D_R0V, ar_next());
+      if (timer) { t_acc += global_ns() - t0; t_cnt++; }
+    }
+    const double alpha = Dl(rn) / Dl(D_R0V);
+    // ---- S
+    if (timer) t_mark = global_ns();
+    {
+      const double* __restrict__ r = A.r;
+      const double* __restrict__ v = A.v;
+      double* __restrict__ sn = A.s;
+      auto sval = [=](size_t j) { return fma(-alpha, v[j], r[j]); };
+      unsigned long long hs = 0;
+      if (A.halo.on) { hs = A.halo.seq0 + (++nhalo); persist_halo_send(A.halo, (int)(hs & 1ull), hs, sval); }
+#pragma unroll 4
+      for (size_t i = first; i < n; i += step) sn[i] = fma(-alpha, v[i], r[i]);
+      if (A.halo.on) persist_halo_recv(A.halo, (int)(hs & 1ull), hs, A.s);
+    }
+    grid_barrier(A.counter, A.flag, ++epoch);
+    if (timer) t_s += global_ns() - t_mark;
+    // ---- S2: t = B A s, <s,t>, <t,t>
+    {
+      unsigned long long t0 = 0;
+      if (timer) t0 = global_ns();
+      double d[2] = {0.0, 0.0};
+      persist_spmv<NV, KMASK, SPMV_DOT_SELF>(A, A.s, A.t, nullptr, nullptr, s_raw, s_bar, gi, d);
+      grid_reduce_barrier(d, 2, A.partial, A.counter, A.flag, ++epoch, D + D_TS, ar_next());
+      if (timer) { t_acc += global_ns() - t0; t_cnt++; }
+    }
+    // ---- XR
+    if (timer) t_mark = global_ns();
+    {
+      const double om = Dl(D_TT) != 0.0 ? Dl(D_TS) / Dl(D_TT) : 0.0;
+      double acc[2] = {0.0, 0.0};
+      double* __restrict__ x = A.x;
+      const double* __restrict__ s = A.s;
+      const double* __restrict__ t = A.t;
+      const double* __restrict__ r0 = A.r0;
+      const double* __restrict__ pp = p;
+      double* __restrict__ r = A.r;
+#pragma unroll 2
+      for (size_t i = first; i < n; i += step) {
+        const double si = s[i];
+        x[i] = fma(om, si, fma(alpha, pp[i], x[i]));
+        const double ri = fma(-om, t[i], si);
+        r[i] = ri;
+        acc[0] = fma(r0[i], ri, acc[0]);
+        acc[1] = fma(ri, ri, acc[1]);
+      }
+      grid_reduce_barrier(acc, 2, A.partial, A.counter, A.flag, ++epoch, D + D_XR0 + 2 * (it & 1), ar_next());
+    }
+    if (timer) t_xr += global_ns() - t_mark;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    A.state[4] = (int)nar;
+    A.state[5] = (int)nhalo;
+    if (A.t_spmv) { A.t_spmv[0] = t_acc; A.t_spmv[1] = t_cnt; A.t_spmv[2] = t_p; A.t_spmv[3] = t_s; A.t_spmv[4] = t_xr; }
+  }
+}
+
+
+template <int NV, unsigned KMASK>
+static int persist_launch(rdc_ctx* c, const PersistArgs& A) {
+  SolverWork* W = c->work;
+  constexpr int SMEM = 2 * SpmvStage<popc_c(KMASK)>::BYTES;
+  auto kern = k_bicgstab_persist<NV, KMASK>;
+  static int grid_dev[64] = {};   // per device: attributes set, co-resident grid size
+  int& grid = grid_dev[c->device & 63];
+  if (grid == 0) {
+    RDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    int per_sm = 0, sms = 0, coop = 0;
+    RDC_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+    RDC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    RDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, RED_THREADS, SMEM));
+    if (!coop || per_sm < 1) { c->err = "cooperative launch is not available for the persistent solver"; return RDC_E_CUDA; }
+    const int want = c->opt.tma_ctas_per_sm > 0 ? c->opt.tma_ctas_per_sm : (NV == 3 ? 6 : 2);
+    grid = sms * (per_sm < want ? per_sm : want);
+    if (grid > SPMV_MAX_GRID) grid = SPMV_MAX_GRID;
+  }
+  W->persist_grid = grid;
+  void* args[] = {(void*)&A};
+  RDC_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(RED_THREADS), args, (size_t)SMEM, c->stream));
+  c->st.kernel_launches++;
+  return 0;
+}
+
+// describe the exchange for one parity of the sequence number without consuming a sequence number (p2p.cu)
+void p2p_fill_halo_args_parity(rdc_ctx* c, HaloArgs* A, int par);
+
+// BiCGStab as ONE cooperative launch (see k_bicgstab_persist).  Needs the TMA tiles; distributed runs need the peer-memory
+// transport (the exchanges happen inside the kernel).  Returns 1 when the caller has to use the five-launch version.
+static int bicgstab_persist(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
+  SolverWork* W = c->work;
+  if (!(W->n_tiles > 0 && c->opt.spmv_tma)) return 1;
+  if (c->S.nranks > 1 && !(p2p_on(c) && c->opt.p2p_fused_ar && c->opt.p2p_fused_halo)) return 1;
+  int rc = ensure_extra_vectors(c);
+  if (rc) return rc;
+  if ((rc = ensure_gmres(c, 1))) return rc;   // borrow V for one more vector
+  if ((rc = halo_exchange(c, c->d_u))) return rc;
+  PersistArgs A;
+  A.n_tiles = W->n_tiles; A.tiles = W->tiles; A.rowptr = c->d_rowptr; A.col = c->d_col; A.val = c->d_val;
+  A.scale = scale; A.b = c->d_rhs;
+  A.n = (size_t)c->S.n_owned * c->nv;
+  A.x = c->d_u; A.r = W->t1; A.r0 = W->t2; A.v = W->t4; A.s = W->hs; A.t = W->V; A.p0 = W->t3; A.p1 = W->hp2;
+  A.partial = W->partial; A.counter = W->counter; A.flag = W->flag + (W->n_persist & 1); A.flag_other = W->flag + ((W->n_persist + 1) & 1);
+  W->n_persist++;
+  A.D = W->h; A.S = W->scal; A.state = W->state;
+  A.rtol = rtol; A.maxits = maxits;
+  A.t_spmv = W->t_spmv;
+  A.ar = ArCtx();
+  A.halo = PersistHalo();
+  P2P* P = c->p2p;
+  if (c->S.nranks > 1) {
+    A.ar.peer = (P2PHeader* const*)P->d_peer;
+    A.ar.mine = (P2PHeader*)P->arena;
+    A.ar.me = c->S.rank;
+    A.ar.nranks = c->S.nranks;
+    A.ar.seq = P->ar_seq;
+    if (!c->S.nbr_rank.empty()) {
+      A.halo.on = 1;
+      p2p_fill_halo_args_parity(c, &A.halo.A[0], 0);
+      p2p_fill_halo_args_parity(c, &A.halo.A[1], 1);
+      A.halo.send_idx = c->d_send_idx;
+      A.halo.hdr = (P2PHeader*)P->arena;
+      A.halo.seq0 = P->halo_seq;
+      A.halo.nv = c->nv;
+    }
+  }
+  switch (c->model) {
+    case RDC_ADPM: rc = persist_launch<3, KM_ADPM>(c, A); break;
+    case RDC_RIPF: rc = persist_launch<3, KM_RIPF>(c, A); break;
+    case RDC_HCC: rc = persist_launch<3, KM_HCC>(c, A); break;
+    case RDC_PIHNA: rc = persist_launch<5, KM_PIHNA>(c, A); break;
+    default: rc = persist_launch<5, KM_PROTEAS>(c, A); break;
+  }
+  if (rc) return rc;
+  unsigned long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  RDC_CUDA(cudaMemcpyAsync(ts, W->t_spmv, sizeof(ts), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = poll(c))) {
+    if (P && c->S.nranks > 1) { P->ar_seq += 1ull << 20; P->halo_seq += 1ull << 20; }   // a failed solve: never reuse its tags
+    return rc;
+  }
+  if (P && c->S.nranks > 1) { P->ar_seq += (unsigned long long)W->h_state[4]; P->halo_seq += (unsigned long long)W->h_state[5]; }
+  *its_out = W->h_state[1];
+  *res_out = W->h_scal[S_RES];
+  c->st.resnorm0 = W->h_scal[S_BNORM];
+  c->st.ms_spmv_total = (double)ts[0] * 1e-6;
+  c->st.n_spmv = (int)ts[1];
+  if (c->opt.trace)
+    fprintf(stderr, "[rdc persist rank %d] its %d grid %d: spmv+reduce %.1f us each, P+barrier %.1f, S+barrier %.1f, XR+reduce %.1f us per iteration\n",
+            c->S.rank, W->h_state[1], W->persist_grid, ts[1] ? ts[0] * 1e-3 / ts[1] : 0.0, W->h_state[1] ? ts[2] * 1e-3 / W->h_state[1] : 0.0,
+            W->h_state[1] ? ts[3] * 1e-3 / W->h_state[1] : 0.0, W->h_state[1] ? ts[4] * 1e-3 / W->h_state[1] : 0.0);
+  if (W->h_state[3]) { c->err = "BiCGStab breakdown"; return RDC_E_DIVERGED; }
+  return 0;
+}
+
 int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int restart, int* its, double* res) {
   const double* scale = nullptr;
   if (pc == RDC_PC_JACOBI) {
@@ -1426,10 +1958,13 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   SolverWork* W = c->work;
   W->n_ev_used = 0;
   int rc;
+  bool persistent = false;   // the persistent solver times its SpMV phases itself (globaltimer inside the kernel)
   if (ksp == RDC_KSP_GMRES) rc = gmres(c, scale, rtol, maxits, restart, its, res);
   else if (ksp == RDC_KSP_CG) rc = pcg(c, scale, rtol, maxits, its, res);
   else if (ksp == RDC_KSP_BICGSTAB) {
-    rc = bicgstab(c, scale, rtol, maxits, its, res);
+    rc = 1;
+    if (c->opt.bicg_persist) { rc = bicgstab_persist(c, scale, rtol, maxits, its, res); persistent = rc != 1; }
+    if (rc == 1) rc = bicgstab(c, scale, rtol, maxits, its, res);
     if (rc == RDC_E_DIVERGED && *res == *res) {
       // rho or omega vanished (not a NaN): the iterate is still valid, continue with the method that cannot break
       // down this way; all ranks take this branch alike because the flags derive from all-reduced values
@@ -1442,7 +1977,7 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   // Every solver ends with a stream synchronisation (the final poll), so the event pairs around the SpMV launches of
   // this solve are complete: sum them now.  Launches issued after convergence return at once (device-side flag) and
   // add ~0, so the mean over the REAL SpMVs is total / (its * spmv per its).
-  {
+  if (!persistent) {
     double tot = 0.0;
     for (int k = 0; k < W->n_ev_used; k++) {
       float ms = 0.f;
@@ -1450,9 +1985,37 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
       else cudaGetLastError();
     }
     c->st.ms_spmv_total = tot;
+    c->st.n_spmv = (*its) * (ksp == RDC_KSP_BICGSTAB ? 2 : 1);
   }
-  c->st.n_spmv = (*its) * (ksp == RDC_KSP_BICGSTAB ? 2 : 1);
   return rc;
+}
+
+// Cost of the persistent solver's grid barriers on this device: `reps` barriers (mode 0) or reduction-barriers (mode 1)
+// back to back in one cooperative launch of 148 x ctas_per_sm CTAs.
+__global__ void __launch_bounds__(RED_THREADS) k_barrier_probe(int reps, int mode, double* partial, unsigned* counter, unsigned* flag,
+                                                               double* out) {
+  unsigned epoch = 0;
+  double acc = 0.0;
+  for (int k = 0; k < reps; k++) {
+    if (mode == 0) grid_barrier(counter, flag, ++epoch);
+    else {
+      double d[2] = {1.0, (double)threadIdx.x};
+      grid_reduce_barrier(d, 2, partial, counter, flag, ++epoch, out, ArCtx());
+      acc += __ldcg(out);
+    }
+  }
+  if (acc < 0.0) out[3] = acc;
+}
+int launch_barrier_probe(rdc_ctx* c, int reps, int ctas_per_sm, int mode) {
+  SolverWork* W = c->work;
+  RDC_CUDA(cudaMemsetAsync(W->flag, 0, 2 * sizeof(unsigned), c->stream));
+  RDC_CUDA(cudaMemsetAsync(W->counter, 0, sizeof(unsigned), c->stream));
+  double* partial = W->partial; unsigned* counter = W->counter; unsigned* flag = W->flag + 1; double* out = W->h + 900;
+  void* args[] = {&reps, &mode, &partial, &counter, &flag, &out};
+  RDC_CUDA(cudaLaunchCooperativeKernel((void*)k_barrier_probe, dim3(148u * ctas_per_sm), dim3(RED_THREADS), args, 0, c->stream));
+  RDC_CUDA(cudaMemsetAsync(W->flag, 0, 2 * sizeof(unsigned), c->stream));   // the solver expects cleared epoch flags
+  c->st.kernel_launches++;
+  return 0;
 }
 
 // Read-only streaming probe over the operator values (16-byte loads, fixed-order reduction): the bandwidth a pure
