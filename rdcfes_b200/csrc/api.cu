@@ -389,6 +389,7 @@ extern "C" int rdc_set_solution(rdc_ctx* c, const double* u) {
   if (!u) return RDC_E_ARG;
   int rc = to_device(c, u, c->d_u);
   if (rc) return rc;
+  c->u_ghost_fresh = true;     // the upload fills the ghost entries as well
   if (c->model == RDC_RIPF) {  // ripf.C:50-51: prev_soln starts as the initial solution
     RDC_CUDA(cudaMemcpyAsync(c->d_prev, c->d_u, (size_t)c->S.n_owned * 3 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->ripf_primed = false;
@@ -445,7 +446,7 @@ extern "C" int rdc_get_old_solution(rdc_ctx* c, double* u) {
 
 extern "C" int rdc_rotate(rdc_ctx* c) {
   CHECK_CTX(c);
-  int rc = halo_exchange(c, c->d_u);  // system.update(): ghosts of the current solution
+  int rc = refresh_u_ghosts(c);  // system.update(): ghosts of the current solution
   if (rc) return rc;
   std::swap(c->d_uolder, c->d_uold);  // older <- old
   RDC_CUDA(cudaMemcpyAsync(c->d_uold, c->d_u, (size_t)c->S.n_loc * c->nv * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -532,6 +533,40 @@ extern "C" int rdc_step(rdc_ctx* c, double time, double dt, int ksp, int pc, dou
   int rc;
   if ((rc = rdc_rotate(c))) return rc;
   if ((rc = rdc_assemble(c, time, dt))) return rc;
+  // BiCGStab runs as one cooperative launch that needs no host decision: the clamp is queued right behind it and the
+  // host synchronises once per step, after both (RIPF's check_solution needs the host and keeps the plain order)
+  if (ksp == RDC_KSP_BICGSTAB && c->model != RDC_RIPF) {
+    resolve_timings(c, false);
+    c->st.n_spmv = 0;
+    cudaEventRecord(c->ev_sol[0], c->stream);
+    rc = solver_persist_begin(c, pc, rtol, maxits);
+    if (rc == 0) {
+      cudaEventRecord(c->ev_sol[1], c->stream);
+      c->t_sol_pending = true;
+      int crc = rdc_clamp(c);
+      int its = 0;
+      double res = 0;
+      rc = solver_persist_end(c, &its, &res);
+      if (rc == RDC_E_DIVERGED && res == res) {
+        // rho or omega vanished: continue with GMRES from the (clamped, still valid) iterate, then clamp again
+        int its2 = 0;
+        rc = rdc_solve(c, RDC_KSP_GMRES, pc, rtol, maxits, restart, &its2, &res);
+        its += its2;
+        if (!rc) crc = rdc_clamp(c);
+      } else {
+        c->st.sum_iterations += its;
+        c->st.sum_n_spmv += c->st.n_spmv;
+        c->st.sum_ms_spmv += c->st.ms_spmv_total;
+        c->st.n_solves++;
+      }
+      c->st.iterations = its;
+      c->st.resnorm = res;
+      if (iterations) *iterations = its;
+      if (resnorm) *resnorm = res;
+      return rc ? rc : crc;
+    }
+    if (rc != 1) return rc;
+  }
   if ((rc = rdc_solve(c, ksp, pc, rtol, maxits, restart, iterations, resnorm))) return rc;
   return rdc_clamp(c);
 }

@@ -142,6 +142,7 @@ struct rdc_ctx {
   double *d_u = nullptr, *d_uold = nullptr, *d_uolder = nullptr;
   double* d_stage = nullptr;         // [D_glob] staging for user vectors in global dof order
   bool assembled = false;
+  bool u_ghost_fresh = false;        // the ghost part of d_u matches the owners' values (distributed runs)
 
   // model state
   double *d_td = nullptr, *d_rt = nullptr, *d_prev = nullptr;   // RIPF: TD [n_loc*3], RT [n_loc*3], prev [n_owned*3]
@@ -181,6 +182,9 @@ void solver_free(rdc_ctx* c);
 int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int restart, int* its, double* res);
 int launch_spmv(rdc_ctx* c, const double* x, double* y, const double* rowscale, bool check_done = false);
 int launch_clamp(rdc_ctx* c);
+int refresh_u_ghosts(rdc_ctx* c);
+int solver_persist_begin(rdc_ctx* c, int pc, double rtol, int maxits);   // 1: not applicable (use solver_solve)
+int solver_persist_end(rdc_ctx* c, int* its, double* res);
 int launch_stream_probe(rdc_ctx* c, int ctas_per_sm);
 int launch_barrier_probe(rdc_ctx* c, int reps, int ctas_per_sm, int mode);
 int spmv_masks_ok();                // solver.cu's entry masks agree with the model definitions

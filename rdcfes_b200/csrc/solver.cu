@@ -61,6 +61,9 @@ struct SolverWork {
   double persist_phase_ms[4] = {0, 0, 0, 0};
   int persist_grid = 0;                 // co-resident CTAs of k_bicgstab_persist on this device (0: not queried yet)
   unsigned long long n_persist = 0;     // persistent solves so far (parity selects the epoch flag)
+  unsigned char* rep = nullptr;         // device report of a persistent solve: 8 doubles (scal) | 8 ints (state) | 8 u64 (timers)
+  unsigned char* h_rep = nullptr;       // its pinned copy
+  bool persist_pending = false;         // a persistent solve has been launched and not yet read back
 };
 
 namespace rdc {
@@ -850,8 +853,17 @@ int launch_pack(rdc_ctx* c, const double* x, int ncomp) {
   return 0;
 }
 
+// ghosts of the current solution: exchanged once after every change of the owned values, not once per consumer
+int refresh_u_ghosts(rdc_ctx* c) {
+  if (c->S.nranks == 1 || c->u_ghost_fresh) return 0;
+  const int rc = halo_exchange(c, c->d_u);
+  if (!rc) c->u_ghost_fresh = true;
+  return rc;
+}
+
 int launch_clamp(rdc_ctx* c) {
   SolverWork* W = c->work;
+  c->u_ghost_fresh = false;
   if (c->model == RDC_RIPF) {
     const double* p = c->params.data();
     const int day = (int)floor(c->time);  // ripf.C:705
@@ -916,6 +928,9 @@ int solver_init(rdc_ctx* c) {
   RDC_CUDA(cudaMalloc(&W->flag, 2 * sizeof(unsigned)));
   RDC_CUDA(cudaMemsetAsync(W->flag, 0, 2 * sizeof(unsigned), c->stream));
   RDC_CUDA(cudaMalloc(&W->t_spmv, 8 * sizeof(unsigned long long)));
+  RDC_CUDA(cudaMalloc(&W->rep, 192));
+  RDC_CUDA(cudaMemsetAsync(W->rep, 0, 192, c->stream));
+  RDC_CUDA(cudaMallocHost(&W->h_rep, 192));
   RDC_CUDA(cudaHostAlloc(&W->h_ring, sizeof(int) * SolverWork::RING, cudaHostAllocMapped));
   memset(W->h_ring, 0, sizeof(int) * SolverWork::RING);
   return 0;
@@ -965,7 +980,7 @@ void solver_free(rdc_ctx* c) {
   cudaFreeHost(W->h_scal); cudaFreeHost(W->h_state);
   for (int k = 0; k < 2 * SolverWork::MAX_EV; k++) cudaEventDestroy(W->ev[k]);
   cudaFreeHost(W->h_ring);
-  cudaFree(W->tiles); cudaFree(W->flag); cudaFree(W->t_spmv);
+  cudaFree(W->tiles); cudaFree(W->flag); cudaFree(W->t_spmv); cudaFree(W->rep); cudaFreeHost(W->h_rep);
   delete W;
   c->work = nullptr;
 }
@@ -1349,7 +1364,7 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
   RDC_CUDA(cudaMemsetAsync(W->state, 0, sizeof(int) * 8, c->stream));
   memset(W->h_ring, 0, sizeof(int) * SolverWork::RING);  // the previous solve ended with a stream synchronisation
   // r = r0 = B (b - A x), <r,r>, ||B b||^2 in one pass over the operator
-  if ((rc = halo_exchange(c, c->d_u))) return rc;
+  if ((rc = refresh_u_ghosts(c))) return rc;
   bool fused;
   {
     const ArCtx ar = ar_begin(c, &fused);
@@ -1844,6 +1859,8 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     A.state[4] = (int)nar;
     A.state[5] = (int)nhalo;
+    A.state[6] = 0;
+    if (A.ar.mine) { A.state[6] = A.ar.mine->error; A.ar.mine->error = 0; }   // a peer wait that timed out: reported once
     if (A.t_spmv) { A.t_spmv[0] = t_acc; A.t_spmv[1] = t_cnt; A.t_spmv[2] = t_p; A.t_spmv[3] = t_s; A.t_spmv[4] = t_xr; }
   }
 }
@@ -1879,14 +1896,14 @@ void p2p_fill_halo_args_parity(rdc_ctx* c, HaloArgs* A, int par);
 
 // BiCGStab as ONE cooperative launch (see k_bicgstab_persist).  Needs the TMA tiles; distributed runs need the peer-memory
 // transport (the exchanges happen inside the kernel).  Returns 1 when the caller has to use the five-launch version.
-static int bicgstab_persist(rdc_ctx* c, const double* scale, double rtol, int maxits, int* its_out, double* res_out) {
+static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, int maxits) {
   SolverWork* W = c->work;
   if (!(W->n_tiles > 0 && c->opt.spmv_tma)) return 1;
   if (c->S.nranks > 1 && !(p2p_on(c) && c->opt.p2p_fused_ar && c->opt.p2p_fused_halo)) return 1;
   int rc = ensure_extra_vectors(c);
   if (rc) return rc;
   if ((rc = ensure_gmres(c, 1))) return rc;   // borrow V for one more vector
-  if ((rc = halo_exchange(c, c->d_u))) return rc;
+  if ((rc = refresh_u_ghosts(c))) return rc;
   PersistArgs A;
   A.n_tiles = W->n_tiles; A.tiles = W->tiles; A.rowptr = c->d_rowptr; A.col = c->d_col; A.val = c->d_val;
   A.scale = scale; A.b = c->d_rhs;
@@ -1894,9 +1911,10 @@ static int bicgstab_persist(rdc_ctx* c, const double* scale, double rtol, int ma
   A.x = c->d_u; A.r = W->t1; A.r0 = W->t2; A.v = W->t4; A.s = W->hs; A.t = W->V; A.p0 = W->t3; A.p1 = W->hp2;
   A.partial = W->partial; A.counter = W->counter; A.flag = W->flag + (W->n_persist & 1); A.flag_other = W->flag + ((W->n_persist + 1) & 1);
   W->n_persist++;
-  A.D = W->h; A.S = W->scal; A.state = W->state;
+  A.D = W->h;
+  A.S = reinterpret_cast<double*>(W->rep); A.state = reinterpret_cast<int*>(W->rep + 64);
+  A.t_spmv = reinterpret_cast<unsigned long long*>(W->rep + 96);
   A.rtol = rtol; A.maxits = maxits;
-  A.t_spmv = W->t_spmv;
   A.ar = ArCtx();
   A.halo = PersistHalo();
   P2P* P = c->p2p;
@@ -1924,25 +1942,50 @@ static int bicgstab_persist(rdc_ctx* c, const double* scale, double rtol, int ma
     default: rc = persist_launch<5, KM_PROTEAS>(c, A); break;
   }
   if (rc) return rc;
-  unsigned long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  RDC_CUDA(cudaMemcpyAsync(ts, W->t_spmv, sizeof(ts), cudaMemcpyDeviceToHost, c->stream));
-  if ((rc = poll(c))) {
+  c->u_ghost_fresh = false;
+  W->persist_pending = true;
+  return 0;
+}
+
+// wait for the launched solve and read its 192-byte report (ONE copy, one synchronisation)
+static int bicgstab_persist_end(rdc_ctx* c, int* its_out, double* res_out) {
+  SolverWork* W = c->work;
+  W->persist_pending = false;
+  P2P* P = c->p2p;
+  cudaError_t e = cudaMemcpyAsync(W->h_rep, W->rep, 192, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  const double* scal = reinterpret_cast<const double*>(W->h_rep);
+  const int* state = reinterpret_cast<const int*>(W->h_rep + 64);
+  const unsigned long long* ts = reinterpret_cast<const unsigned long long*>(W->h_rep + 96);
+  if (e != cudaSuccess) {
     if (P && c->S.nranks > 1) { P->ar_seq += 1ull << 20; P->halo_seq += 1ull << 20; }   // a failed solve: never reuse its tags
-    return rc;
+    c->err = std::string("persistent BiCGStab: ") + cudaGetErrorString(e);
+    return RDC_E_CUDA;
   }
-  if (P && c->S.nranks > 1) { P->ar_seq += (unsigned long long)W->h_state[4]; P->halo_seq += (unsigned long long)W->h_state[5]; }
-  *its_out = W->h_state[1];
-  *res_out = W->h_scal[S_RES];
-  c->st.resnorm0 = W->h_scal[S_BNORM];
+  if (P && c->S.nranks > 1) { P->ar_seq += (unsigned long long)state[4]; P->halo_seq += (unsigned long long)state[5]; }
+  memcpy(W->h_state, state, sizeof(int) * 8);
+  memcpy(W->h_scal, scal, sizeof(double) * 8);
+  *its_out = state[1];
+  *res_out = scal[S_RES];
+  c->st.resnorm0 = scal[S_BNORM];
   c->st.ms_spmv_total = (double)ts[0] * 1e-6;
   c->st.n_spmv = (int)ts[1];
   if (c->opt.trace)
     fprintf(stderr, "[rdc persist rank %d] its %d grid %d: spmv+reduce %.1f us each, P+barrier %.1f, S+barrier %.1f, XR+reduce %.1f us per iteration\n",
-            c->S.rank, W->h_state[1], W->persist_grid, ts[1] ? ts[0] * 1e-3 / ts[1] : 0.0, W->h_state[1] ? ts[2] * 1e-3 / W->h_state[1] : 0.0,
-            W->h_state[1] ? ts[3] * 1e-3 / W->h_state[1] : 0.0, W->h_state[1] ? ts[4] * 1e-3 / W->h_state[1] : 0.0);
-  if (W->h_state[3]) { c->err = "BiCGStab breakdown"; return RDC_E_DIVERGED; }
+            c->S.rank, state[1], W->persist_grid, ts[1] ? ts[0] * 1e-3 / ts[1] : 0.0, state[1] ? ts[2] * 1e-3 / state[1] : 0.0,
+            state[1] ? ts[3] * 1e-3 / state[1] : 0.0, state[1] ? ts[4] * 1e-3 / state[1] : 0.0);
+  if (state[6]) { c->err = "peer-memory exchange timed out (a rank did not arrive); ghost values are stale"; return RDC_E_COMM; }
+  if (state[3]) { c->err = "BiCGStab breakdown"; return RDC_E_DIVERGED; }
   return 0;
 }
+
+// the two halves for rdc_step (api.cu): between them the caller may queue work that does not need the host (the clamp)
+int solver_persist_begin(rdc_ctx* c, int pc, double rtol, int maxits) {
+  if (!c->opt.bicg_persist || (pc != RDC_PC_JACOBI && pc != RDC_PC_NONE) || maxits < 0) return 1;
+  c->work->n_ev_used = 0;
+  return bicgstab_persist_begin(c, pc == RDC_PC_JACOBI ? c->d_dinv : nullptr, rtol, maxits);
+}
+int solver_persist_end(rdc_ctx* c, int* its, double* res) { return bicgstab_persist_end(c, its, res); }
 
 int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int restart, int* its, double* res) {
   const double* scale = nullptr;
@@ -1963,7 +2006,11 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   else if (ksp == RDC_KSP_CG) rc = pcg(c, scale, rtol, maxits, its, res);
   else if (ksp == RDC_KSP_BICGSTAB) {
     rc = 1;
-    if (c->opt.bicg_persist) { rc = bicgstab_persist(c, scale, rtol, maxits, its, res); persistent = rc != 1; }
+    if (c->opt.bicg_persist) {
+      rc = bicgstab_persist_begin(c, scale, rtol, maxits);
+      persistent = rc != 1;
+      if (rc == 0) rc = bicgstab_persist_end(c, its, res);
+    }
     if (rc == 1) rc = bicgstab(c, scale, rtol, maxits, its, res);
     if (rc == RDC_E_DIVERGED && *res == *res) {
       // rho or omega vanished (not a NaN): the iterate is still valid, continue with the method that cannot break
@@ -1977,6 +2024,7 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   // Every solver ends with a stream synchronisation (the final poll), so the event pairs around the SpMV launches of
   // this solve are complete: sum them now.  Launches issued after convergence return at once (device-side flag) and
   // add ~0, so the mean over the REAL SpMVs is total / (its * spmv per its).
+  c->u_ghost_fresh = false;   // the solution changed
   if (!persistent) {
     double tot = 0.0;
     for (int k = 0; k < W->n_ev_used; k++) {
