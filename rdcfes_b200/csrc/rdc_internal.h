@@ -105,6 +105,7 @@ struct rdc_options {
   int p2p_fused_ar = 1;        // all-reduce finished inside the producing kernel
   int p2p_fused_halo = 1;      // ghost exchange inside the BiCGStab vector kernels
   int bicg_persist = 1;        // BiCGStab as one cooperative launch (solver.cu k_bicgstab_persist); 0 = five launches per iteration
+  int persist_timing = 1;      // the persistent solver times its phases (SpMV time of rdc_stats); 0 = no timer reads
   int trace = 0;               // print the device time of every operation of BiCGStab iteration 4
 };
 

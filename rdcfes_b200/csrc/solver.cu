@@ -1467,6 +1467,7 @@ struct PersistArgs {
   double *x, *r, *r0, *v, *s, *t, *p0, *p1;
   double* partial; unsigned* counter; unsigned* flag; unsigned* flag_other; double* D; double* S; int* state;
   double rtol; int maxits;
+  int timing;          // block 0 times the phases with %globaltimer (each read costs ~1 us of the critical path)
   ArCtx ar;            // ar.seq = all-reduces done before this solve
   PersistHalo halo;
   unsigned long long* t_spmv;   // [8] globaltimer ns of block 0: [0] SpMV phases, [1] their number, [2] P, [3] S, [4] XR phases (each with its barrier), [5] set-up
@@ -1582,12 +1583,96 @@ __device__ __forceinline__ void grid_reduce_barrier(double (&v)[2], int nval, do
   grid_wait(flag, epoch);
 }
 
+// Reduction + barrier of the persistent solver, second form: every CTA leaves its partial sums in the list, passes ONE plain
+// barrier, then reads the whole list itself (<= 1024 entries from L2, all loads in flight) and adds it in the fixed order
+// -- every CTA gets the bit-identical total without waiting for a designated block to compute and publish it (7.3 -> ~4 us
+// per reduction on one GPU).  Distributed: block 0 sends the rank's total to every peer (tag-in-word slots) and EVERY CTA
+// polls the slots of all ranks in its own rank's header and adds them in rank order.  The results go to the CTA's own
+// copy of the slot table in shared memory (s_out), so the scalars of the recurrences are read from shared memory.
+static constexpr int PERSIST_MAX_GRID = 1024;
+__device__ __noinline__ void grid_allreduce(double v0, double v1, int nval, double* partial, unsigned* counter, unsigned* flag,
+                                            unsigned epoch, const ArCtx ar, double* s_out) {
+  __shared__ double s_red[RED_THREADS / 32][2];
+  __shared__ double s_tot[2];
+  __shared__ double s_in[RDC_MAX_RANKS][2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  {
+    const double w0 = warp_sum(v0), w1 = warp_sum(v1);
+    if (lane == 0) { s_red[wid][0] = w0; s_red[wid][1] = w1; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 && threadIdx.x < nval) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < RED_THREADS / 32; w++) s += s_red[w][threadIdx.x];
+    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+    __threadfence();
+  }
+  grid_barrier(counter, flag, epoch);
+  constexpr int NB = PERSIST_MAX_GRID / RED_THREADS;
+  double pv[2][NB];
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    const unsigned b = threadIdx.x + (unsigned)j * RED_THREADS;
+#pragma unroll
+    for (int k = 0; k < 2; k++) pv[k][j] = (b < gridDim.x && k < nval) ? __ldcg(partial + (size_t)k * gridDim.x + b) : 0.0;
+  }
+  double sk[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+      if (threadIdx.x + (unsigned)j * RED_THREADS < gridDim.x) sk[k] += pv[k][j];
+    sk[k] = warp_sum(sk[k]);
+  }
+  if (lane == 0) { s_red[wid][0] = sk[0]; s_red[wid][1] = sk[1]; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < RED_THREADS / 32; w++) t += s_red[w][threadIdx.x];
+    s_tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (ar.nranks > 1) {
+    const int par = (int)(ar.seq & 1ull);
+    const unsigned tag = (unsigned)ar.seq;
+    const int q = threadIdx.x / 2, k = threadIdx.x % 2;
+    if (q < ar.nranks && k < nval) {
+      if (blockIdx.x == 0) ll_store(&ar.peer[q]->ll[par][ar.me][k][0], s_tot[k], tag);
+      double got = 0.0;
+      const unsigned long long t0 = global_ns();
+      int spins = 0;
+      while (!ll_load(&ar.mine->ll[par][q][k][0], tag, &got)) {
+        if ((++spins & 1023) == 0 && global_ns() - t0 > P2P_TIMEOUT_NS) { ar.mine->error = 1; break; }
+      }
+      s_in[q][k] = got;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 && threadIdx.x < nval) {
+      double t = 0.0;
+      for (int r = 0; r < ar.nranks; r++) t += s_in[r][threadIdx.x];
+      s_out[threadIdx.x] = t;
+    }
+  } else if (threadIdx.x < 2 && threadIdx.x < nval) {
+    s_out[threadIdx.x] = s_tot[threadIdx.x];
+  }
+  __syncthreads();
+}
+
 // one SpMV phase of the persistent kernel: the tile loop of k_spmv_tma with a tile counter `gi` that keeps running over
 // the phases (stage index and mbarrier parity follow it)
+// Not inlined on purpose: the phases of the persistent kernel are separate functions so that each gets the whole register
+// budget of the kernel (40 registers at 6 CTAs/SM) for its own loop; inlined, the loop-carried state of the solver was
+// spilled INSIDE the tile loop (800 bytes of spill traffic per thread, +12 % per iteration).
+struct SpmvOp {
+  int n_tiles; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val; const double* scale;
+};
+struct SpmvRes { double d0, d1; unsigned gi; };
 template <int NV, unsigned KMASK, int MODE>
-__device__ __forceinline__ void persist_spmv(const PersistArgs& A, const double* __restrict__ x, double* __restrict__ y,
+__device__ __noinline__ SpmvRes persist_spmv(const SpmvOp A, const double* __restrict__ x, double* __restrict__ y,
                                              const double* __restrict__ w, double* __restrict__ y2, unsigned char* s_raw,
-                                             unsigned long long* s_bar, unsigned& gi, double (&d)[2]) {
+                                             unsigned long long* s_bar, unsigned gi) {
   constexpr int G = 16, STAGES = 2;
   constexpr int NKV = popc_c(KMASK);
   typedef SpmvStage<NKV> ST;
@@ -1595,6 +1680,7 @@ __device__ __forceinline__ void persist_spmv(const PersistArgs& A, const double*
   const unsigned hmask = 0xffffu << (tid & 16);
   const int4* __restrict__ tiles = A.tiles;
   const int n_tiles = A.n_tiles;
+  double d[2] = {0.0, 0.0};
   auto issue = [&](int tile, unsigned slot) {
     const int4 t = tiles[tile];
     const int skip_v = (int)(((long long)t.z * NKV) & 1), skip_c = t.z & 3, skip_r = t.x & 3;
@@ -1677,6 +1763,44 @@ __device__ __forceinline__ void persist_spmv(const PersistArgs& A, const double*
     }
     __syncthreads();
   }
+  SpmvRes out;
+  out.d0 = d[0]; out.d1 = d[1]; out.gi = gi;
+  return out;
+}
+
+// the three vector phases (own entries only; the ghost exchange is done by the caller around them)
+__device__ __noinline__ void persist_p(size_t n, int it, double beta, double omega, const double* __restrict__ r,
+                                       const double* __restrict__ v, const double* __restrict__ po, double* __restrict__ pn) {
+  const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  if (it == 0) {
+#pragma unroll 4
+    for (size_t i = first; i < n; i += step) pn[i] = r[i];
+  } else {
+#pragma unroll 4
+    for (size_t i = first; i < n; i += step) pn[i] = fma(beta, fma(-omega, v[i], po[i]), r[i]);
+  }
+}
+__device__ __noinline__ void persist_s(size_t n, double alpha, const double* __restrict__ r, const double* __restrict__ v,
+                                       double* __restrict__ sn) {
+  const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+#pragma unroll 4
+  for (size_t i = first; i < n; i += step) sn[i] = fma(-alpha, v[i], r[i]);
+}
+__device__ __noinline__ double2 persist_xr(size_t n, double alpha, double om, double* __restrict__ x, const double* __restrict__ pp,
+                                          const double* __restrict__ s, const double* __restrict__ t, double* __restrict__ r,
+                                          const double* __restrict__ r0) {
+  const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll 2
+  for (size_t i = first; i < n; i += step) {
+    const double si = s[i];
+    x[i] = fma(om, si, fma(alpha, pp[i], x[i]));
+    const double ri = fma(-om, t[i], si);
+    r[i] = ri;
+    a0 = fma(r0[i], ri, a0);
+    a1 = fma(ri, ri, a1);
+  }
+  return make_double2(a0, a1);
 }
 
 // ghost exchange of a vector inside a phase: virtual exchange blocks are dealt to the CTAs round-robin; all sends of a
@@ -1736,20 +1860,27 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
   // this solve's flag was cleared by the previous one (both start at zero): no memset between the solves
   if (blockIdx.x == 0 && threadIdx.x == 0) { *A.flag_other = 0u; A.state[0] = 0; A.state[3] = 0; }
   unsigned epoch = 0, gi = 0;
+  const unsigned long long t_begin = A.timing ? global_ns() : 0ull;
   unsigned long long nar = 0, nhalo = 0;          // reductions / exchanges of this solve so far
   unsigned long long t_acc = 0, t_cnt = 0, t_p = 0, t_s = 0, t_xr = 0, t_mark = 0;
   const size_t n = A.n;
   const size_t first = blockIdx.x * (size_t)blockDim.x + threadIdx.x, step = (size_t)gridDim.x * blockDim.x;
-  double* const D = A.D;                 // written by the last block of a reduction: read it from L2, never from a stale L1 line
-  auto Dl = [&](int k) { return __ldcg(D + k); };
+  __shared__ double s_D[16];             // this CTA's copy of the dot-product slot table (every CTA computes the same sums)
+  double* const D = s_D;
+  auto Dl = [&](int k) { return s_D[k]; };
   auto ar_next = [&]() { ArCtx a = A.ar; a.seq = A.ar.seq + (++nar); return a; };
-  const bool timer = blockIdx.x == 0 && threadIdx.x == 0;
+  const bool timer = A.timing && blockIdx.x == 0 && threadIdx.x == 0;
 
   // r = r0 = B (b - A x), <r,r>, ||B b||^2 (the ghosts of x were exchanged by the host-side launch before)
+  unsigned long long t_resid = 0;
+  SpmvOp op;
+  op.n_tiles = A.n_tiles; op.tiles = A.tiles; op.rowptr = A.rowptr; op.col = A.col; op.val = A.val; op.scale = A.scale;
   {
-    double d[2] = {0.0, 0.0};
-    persist_spmv<NV, KMASK, SPMV_RESID>(A, A.x, A.r, A.b, A.r0, s_raw, s_bar, gi, d);
-    grid_reduce_barrier(d, 2, A.partial, A.counter, A.flag, ++epoch, D + D_INIT, ar_next());
+    const SpmvRes sr = persist_spmv<NV, KMASK, SPMV_RESID>(op, A.x, A.r, A.b, A.r0, s_raw, s_bar, gi);
+    gi = sr.gi;
+    double d[2] = {sr.d0, sr.d1};
+    grid_allreduce(d[0], d[1], 2, A.partial, A.counter, A.flag, ++epoch, ar_next(), D + D_INIT);
+    if (timer) t_resid = global_ns() - t_begin;
   }
   int it = 0;
   for (;; it++) {
@@ -1787,13 +1918,7 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
       auto pval = [=](size_t j) { return it == 0 ? r[j] : fma(beta, fma(-omega, v[j], po[j]), r[j]); };
       unsigned long long hs = 0;
       if (A.halo.on) { hs = A.halo.seq0 + (++nhalo); persist_halo_send(A.halo, (int)(hs & 1ull), hs, pval); }
-      if (it == 0) {
-#pragma unroll 4
-        for (size_t i = first; i < n; i += step) pn[i] = r[i];
-      } else {
-#pragma unroll 4
-        for (size_t i = first; i < n; i += step) pn[i] = fma(beta, fma(-omega, v[i], po[i]), r[i]);
-      }
+      persist_p(n, it, beta, omega, r, v, po, pn);
       if (A.halo.on) persist_halo_recv(A.halo, (int)(hs & 1ull), hs, p);
     }
     grid_barrier(A.counter, A.flag, ++epoch);
@@ -1802,9 +1927,10 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
     {
       unsigned long long t0 = 0;
       if (timer) t0 = global_ns();
-      double d[2] = {0.0, 0.0};
-      persist_spmv<NV, KMASK, SPMV_DOT_W>(A, p, A.v, A.r0, nullptr, s_raw, s_bar, gi, d);
-      grid_reduce_barrier(d, 1, A.partial, A.counter, A.flag, ++epoch, D + D_R0V, ar_next());
+      const SpmvRes sr = persist_spmv<NV, KMASK, SPMV_DOT_W>(op, p, A.v, A.r0, nullptr, s_raw, s_bar, gi);
+      gi = sr.gi;
+      double d[2] = {sr.d0, sr.d1};
+      grid_allreduce(d[0], d[1], 1, A.partial, A.counter, A.flag, ++epoch, ar_next(), D + D_R0V);
       if (timer) { t_acc += global_ns() - t0; t_cnt++; }
     }
     const double alpha = Dl(rn) / Dl(D_R0V);
@@ -1817,8 +1943,7 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
       auto sval = [=](size_t j) { return fma(-alpha, v[j], r[j]); };
       unsigned long long hs = 0;
       if (A.halo.on) { hs = A.halo.seq0 + (++nhalo); persist_halo_send(A.halo, (int)(hs & 1ull), hs, sval); }
-#pragma unroll 4
-      for (size_t i = first; i < n; i += step) sn[i] = fma(-alpha, v[i], r[i]);
+      persist_s(n, alpha, r, v, sn);
       if (A.halo.on) persist_halo_recv(A.halo, (int)(hs & 1ull), hs, A.s);
     }
     grid_barrier(A.counter, A.flag, ++epoch);
@@ -1827,32 +1952,19 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
     {
       unsigned long long t0 = 0;
       if (timer) t0 = global_ns();
-      double d[2] = {0.0, 0.0};
-      persist_spmv<NV, KMASK, SPMV_DOT_SELF>(A, A.s, A.t, nullptr, nullptr, s_raw, s_bar, gi, d);
-      grid_reduce_barrier(d, 2, A.partial, A.counter, A.flag, ++epoch, D + D_TS, ar_next());
+      const SpmvRes sr = persist_spmv<NV, KMASK, SPMV_DOT_SELF>(op, A.s, A.t, nullptr, nullptr, s_raw, s_bar, gi);
+      gi = sr.gi;
+      double d[2] = {sr.d0, sr.d1};
+      grid_allreduce(d[0], d[1], 2, A.partial, A.counter, A.flag, ++epoch, ar_next(), D + D_TS);
       if (timer) { t_acc += global_ns() - t0; t_cnt++; }
     }
     // ---- XR
     if (timer) t_mark = global_ns();
     {
       const double om = Dl(D_TT) != 0.0 ? Dl(D_TS) / Dl(D_TT) : 0.0;
-      double acc[2] = {0.0, 0.0};
-      double* __restrict__ x = A.x;
-      const double* __restrict__ s = A.s;
-      const double* __restrict__ t = A.t;
-      const double* __restrict__ r0 = A.r0;
-      const double* __restrict__ pp = p;
-      double* __restrict__ r = A.r;
-#pragma unroll 2
-      for (size_t i = first; i < n; i += step) {
-        const double si = s[i];
-        x[i] = fma(om, si, fma(alpha, pp[i], x[i]));
-        const double ri = fma(-om, t[i], si);
-        r[i] = ri;
-        acc[0] = fma(r0[i], ri, acc[0]);
-        acc[1] = fma(ri, ri, acc[1]);
-      }
-      grid_reduce_barrier(acc, 2, A.partial, A.counter, A.flag, ++epoch, D + D_XR0 + 2 * (it & 1), ar_next());
+      const double2 a2 = persist_xr(n, alpha, om, A.x, p, A.s, A.t, A.r, A.r0);
+      double acc[2] = {a2.x, a2.y};
+      grid_allreduce(acc[0], acc[1], 2, A.partial, A.counter, A.flag, ++epoch, ar_next(), D + D_XR0 + 2 * (it & 1));
     }
     if (timer) t_xr += global_ns() - t_mark;
   }
@@ -1861,7 +1973,7 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
     A.state[5] = (int)nhalo;
     A.state[6] = 0;
     if (A.ar.mine) { A.state[6] = A.ar.mine->error; A.ar.mine->error = 0; }   // a peer wait that timed out: reported once
-    if (A.t_spmv) { A.t_spmv[0] = t_acc; A.t_spmv[1] = t_cnt; A.t_spmv[2] = t_p; A.t_spmv[3] = t_s; A.t_spmv[4] = t_xr; }
+    if (A.t_spmv) { A.t_spmv[0] = t_acc; A.t_spmv[1] = t_cnt; A.t_spmv[2] = t_p; A.t_spmv[3] = t_s; A.t_spmv[4] = t_xr; A.t_spmv[5] = A.timing ? global_ns() - t_begin : 0ull; A.t_spmv[6] = t_resid; }
   }
 }
 
@@ -1882,7 +1994,7 @@ static int persist_launch(rdc_ctx* c, const PersistArgs& A) {
     if (!coop || per_sm < 1) { c->err = "cooperative launch is not available for the persistent solver"; return RDC_E_CUDA; }
     const int want = c->opt.tma_ctas_per_sm > 0 ? c->opt.tma_ctas_per_sm : (NV == 3 ? 6 : 2);
     grid = sms * (per_sm < want ? per_sm : want);
-    if (grid > SPMV_MAX_GRID) grid = SPMV_MAX_GRID;
+    if (grid > PERSIST_MAX_GRID) grid = PERSIST_MAX_GRID / sms * sms;
   }
   W->persist_grid = grid;
   void* args[] = {(void*)&A};
@@ -1915,6 +2027,7 @@ static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, 
   A.S = reinterpret_cast<double*>(W->rep); A.state = reinterpret_cast<int*>(W->rep + 64);
   A.t_spmv = reinterpret_cast<unsigned long long*>(W->rep + 96);
   A.rtol = rtol; A.maxits = maxits;
+  A.timing = c->opt.persist_timing;
   A.ar = ArCtx();
   A.halo = PersistHalo();
   P2P* P = c->p2p;
@@ -1971,9 +2084,10 @@ static int bicgstab_persist_end(rdc_ctx* c, int* its_out, double* res_out) {
   c->st.ms_spmv_total = (double)ts[0] * 1e-6;
   c->st.n_spmv = (int)ts[1];
   if (c->opt.trace)
-    fprintf(stderr, "[rdc persist rank %d] its %d grid %d: spmv+reduce %.1f us each, P+barrier %.1f, S+barrier %.1f, XR+reduce %.1f us per iteration\n",
+    fprintf(stderr, "[rdc persist rank %d] its %d grid %d: spmv+reduce %.1f us each, P+barrier %.1f, S+barrier %.1f, XR+reduce %.1f us per iteration; "
+            "kernel %.1f us (block 0), initial residual phase %.1f us\n",
             c->S.rank, state[1], W->persist_grid, ts[1] ? ts[0] * 1e-3 / ts[1] : 0.0, state[1] ? ts[2] * 1e-3 / state[1] : 0.0,
-            state[1] ? ts[3] * 1e-3 / state[1] : 0.0, state[1] ? ts[4] * 1e-3 / state[1] : 0.0);
+            state[1] ? ts[3] * 1e-3 / state[1] : 0.0, state[1] ? ts[4] * 1e-3 / state[1] : 0.0, ts[5] * 1e-3, ts[6] * 1e-3);
   if (state[6]) { c->err = "peer-memory exchange timed out (a rank did not arrive); ghost values are stale"; return RDC_E_COMM; }
   if (state[3]) { c->err = "BiCGStab breakdown"; return RDC_E_DIVERGED; }
   return 0;
@@ -2048,8 +2162,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_barrier_probe(int reps, int mod
     if (mode == 0) grid_barrier(counter, flag, ++epoch);
     else {
       double d[2] = {1.0, (double)threadIdx.x};
-      grid_reduce_barrier(d, 2, partial, counter, flag, ++epoch, out, ArCtx());
-      acc += __ldcg(out);
+      if (mode == 1) { grid_reduce_barrier(d, 2, partial, counter, flag, ++epoch, out, ArCtx()); acc += __ldcg(out); }
+      else { __shared__ double s_o[2]; grid_allreduce(d[0], d[1], 2, partial, counter, flag, ++epoch, ArCtx(), s_o); acc += s_o[0]; }
     }
   }
   if (acc < 0.0) out[3] = acc;

@@ -123,7 +123,12 @@ def main():
             st = gpu.stats()
             print(f"{cases.NAMES[model]} x{world}: rel L2 vs oracle after {nsteps} steps {rel:.2e}; owned {st.n_nodes_local} "
                   f"ghost {st.n_nodes_ghost}", flush=True)
-            if not rel <= 1e-8:
+            # north_star tolerances: every single step 1e-8, the state after N steps 1e-6.  RIPF switches source terms on the
+            # sign of a time derivative that is round-off noise where nothing changes (ripf.C:491-496), so two converged
+            # Krylov solvers may take different branches there after the first step: 2e-8 on the 8-rank mesh
+            if not trace[0][2] <= 1e-8:
+                failures.append(f"{cases.NAMES[model]}: first-step solution rel L2 {trace[0][2]:.3e}")
+            if not rel <= (1e-6 if model == cases.RIPF else 1e-8):
                 failures.append(f"{cases.NAMES[model]}: solution rel L2 {rel:.3e}")
         gpu.close()
     flag = torch.tensor([len(failures)], device="cuda")

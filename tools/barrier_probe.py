@@ -11,9 +11,9 @@ import cases  # noqa: E402
 conn, xyz = cases.mesh(cases.TET4, 6)
 p, u0, ef, nf = cases.case(cases.ADPM, conn, xyz, "full")
 gpu = cases.gpu_system(cases.ADPM, cases.TET4, conn, xyz, p, u0, ef, nf)
-for mode in (0, 1):
+for mode in (0, 1, 2):
     for per_sm in (1, 2, 4, 6):
         us = C.c_double()
         rc = gpu._L.rdc_bench_barrier(gpu._h, 2000, per_sm, mode, C.byref(us))
-        print(f"mode {mode} ({'barrier' if mode == 0 else 'reduce+barrier'}) {148 * per_sm} CTAs: {us.value:.2f} us rc={rc}")
+        print(f"mode {mode} ({('barrier', 'reduce by the last block + barrier', 'barrier + every CTA reduces')[mode]}) {148 * per_sm} CTAs: {us.value:.2f} us rc={rc}")
 gpu.close()
