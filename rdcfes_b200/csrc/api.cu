@@ -24,7 +24,7 @@ static const OptName kOptions[] = {
     {"spmv_ctas_per_sm", &rdc_options::spmv_ctas_per_sm}, {"tma_ctas_per_sm", &rdc_options::tma_ctas_per_sm},
     {"tma_stages", &rdc_options::tma_stages}, {"sync_every", &rdc_options::sync_every},
     {"p2p_fused_ar", &rdc_options::p2p_fused_ar}, {"p2p_fused_halo", &rdc_options::p2p_fused_halo},
-    {"bicg_persist", &rdc_options::bicg_persist}, {"persist_timing", &rdc_options::persist_timing}, {"trace", &rdc_options::trace}};
+    {"node_order", &rdc_options::node_order}, {"bicg_persist", &rdc_options::bicg_persist}, {"persist_timing", &rdc_options::persist_timing}, {"trace", &rdc_options::trace}};
 
 static void options_from_env(rdc_options& o) {
   for (const OptName& k : kOptions) {
@@ -105,7 +105,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
   int rc = 0;
   auto fail = [&](int code) { g_create_err = c->err; rdc_destroy(c); return code; };
   try {
-    rc = build_setup(c->S, elem_type, nv, N, E, conn, xyz, rank, nranks, partitioner, pairs_per_cta_for(model, elem_type), c->err);
+    rc = build_setup(c->S, elem_type, nv, N, E, conn, xyz, rank, nranks, partitioner, pairs_per_cta_for(model, elem_type), c->opt.node_order, c->err);
   } catch (const std::bad_alloc&) { c->err = "out of host memory in set-up"; rc = RDC_E_NOMEM; }
   if (rc) return fail(rc);
   HostSetup& S = c->S;
@@ -120,6 +120,8 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     }
   }
   if (nranks > 1) c->identity_dofs = false;
+  for (int32_t l = 0; l < c->S.n_owned && c->identity_dofs; l++)
+    if (c->S.loc2glob[l] != l) c->identity_dofs = false;   // Morton numbering: user vectors go through the dof map
 
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return fail(RDC_E_CUDA); }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
@@ -176,6 +178,12 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
       for (int a = 0; a < nv; a++) dm[(size_t)l * nv + a] = base + a;
     }
     if ((r = upload(c, &c->d_dofmap, dm))) return r;
+    {  // local nodes sorted by the global dof they map to: zero-copy transfers walk host memory in ascending order
+      std::vector<int32_t> by((size_t)S.n_loc);
+      for (int32_t l = 0; l < S.n_loc; l++) by[l] = l;
+      std::sort(by.begin(), by.end(), [&](int32_t a, int32_t b) { return dm[(size_t)a * nv] < dm[(size_t)b * nv]; });
+      if ((r = upload(c, &c->d_node_by_glob, by))) return r;
+    }
     const size_t vb = (size_t)S.n_loc * nv * sizeof(double);
     if ((r = vec_alloc(&c->d_u, (size_t)S.n_loc * nv))) return r;
     RDC_CUDA(cudaMalloc(&c->d_uold, vb)); RDC_CUDA(cudaMalloc(&c->d_uolder, vb));
@@ -248,7 +256,7 @@ extern "C" void rdc_destroy(rdc_ctx* c) {
   comm_destroy(c);
   cudaFree(c->d_conn); cudaFree(c->d_xyz); cudaFree(c->d_efield); cudaFree(c->d_n2e_ptr); cudaFree(c->d_pair);
   cudaFree(c->d_rowptr); cudaFree(c->d_col); cudaFree(c->d_diag_blk); cudaFree(c->d_cta_node); cudaFree(c->d_task);
-  cudaFree(c->d_clist); cudaFree(c->d_dofmap); cudaFree(c->d_val); cudaFree(c->d_rhs); cudaFree(c->d_dinv);
+  cudaFree(c->d_clist); cudaFree(c->d_dofmap); cudaFree(c->d_node_by_glob); cudaFree(c->d_val); cudaFree(c->d_rhs); cudaFree(c->d_dinv);
   cudaFree(c->d_u); cudaFree(c->d_uold); cudaFree(c->d_uolder); cudaFree(c->d_stage); cudaFree(c->d_td); cudaFree(c->d_rt);
   cudaFree(c->d_prev); cudaFree(c->d_aux); cudaFree(c->d_send_idx); cudaFree(c->d_sendbuf);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -358,7 +366,7 @@ static int to_device(rdc_ctx* c, const double* host, double* d_loc) {
     RDC_CUDA(cudaMemcpyAsync(d_loc, host, (size_t)c->D_glob * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     return 0;
   }
-  if (host_is_mapped(host)) {
+  if (c->S.nranks > 1 && host_is_mapped(host)) {
     // a rank needs only its own n_loc*v entries: gather them straight out of the pinned host buffer instead of
     // staging the whole global vector (distributed runs move 1/nranks of the bytes)
     cudaPointerAttributes a;
@@ -756,7 +764,7 @@ extern "C" int rdc_probe_partition(int elem_type, int nvars, int64_t n_nodes, in
   std::string err;
   int rc;
   try {
-    rc = build_setup(S, elem_type, nvars, n_nodes, n_elems, conn, xyz, rank, nranks, partitioner, 256, err);
+    rc = build_setup(S, elem_type, nvars, n_nodes, n_elems, conn, xyz, rank, nranks, partitioner, 256, 1, err);
   } catch (const std::bad_alloc&) { rc = RDC_E_NOMEM; err = "out of host memory"; }
   if (rc) { g_create_err = err; return rc; }
   *n_owned = S.n_owned; *n_ghost = S.n_ghost; *n_elems_local = S.E_loc;

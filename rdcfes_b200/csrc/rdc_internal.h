@@ -82,7 +82,7 @@ struct HostSetup {
 
 // partitioner: 0 = METIS k-way on the nodal graph, 1 = recursive coordinate bisection
 int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const int32_t* conn, const double* xyz,
-                int rank, int nranks, int partitioner, int pairs_per_cta, std::string& err);
+                int rank, int nranks, int partitioner, int pairs_per_cta, int node_order, std::string& err);
 
 bool cut_spmv_tiles(const int32_t* rowptr, int32_t n_rows, int max_rows, int max_blocks, std::vector<int32_t>& tiles);
 void bucket_regions(int64_t E_loc, const uint8_t* counted, const int32_t* region_of_local, int n_regions, int chunk,
@@ -104,6 +104,7 @@ struct rdc_options {
   int sync_every = 0;          // iterations queued ahead of the convergence flag (0 = default)
   int p2p_fused_ar = 1;        // all-reduce finished inside the producing kernel
   int p2p_fused_halo = 1;      // ghost exchange inside the BiCGStab vector kernels
+  int node_order = 1;          // local numbering of the owned nodes: 1 Morton curve of the coordinates, 0 ascending global id (read at rdc_create)
   int bicg_persist = 1;        // BiCGStab as one cooperative launch (solver.cu k_bicgstab_persist); 0 = five launches per iteration
   int persist_timing = 1;      // the persistent solver times its phases (SpMV time of rdc_stats); 0 = no timer reads
   int trace = 0;               // print the device time of every operation of BiCGStab iteration 4
@@ -130,6 +131,7 @@ struct rdc_ctx {
   int32_t *d_cta_node = nullptr, *d_task = nullptr;
   uint16_t* d_clist = nullptr;
   int32_t* d_dofmap = nullptr;       // [n_loc*nv] global dof id of each local dof (gather/scatter of user vectors)
+  int32_t* d_node_by_glob = nullptr; // [n_loc] local node ids in ascending order of their global dof base (host-memory side of zero-copy transfers)
   int ncta = 0;
   int64_t nnzb = 0;
   // structurally non-zero entries (a,b) of the model's v x v node block (bit a*nv+b).  Only these NKV entry

@@ -133,8 +133,19 @@ static int partition_nodes(int64_t N, int64_t E, int nen, const int32_t* conn, c
 }
 
 // ---- the full set-up --------------------------------------------------------------------------
+// 63-bit Morton key of a point quantised to 21 bits per axis inside the bounding box [lo, lo + 1/inv)
+static inline uint64_t spread21(uint64_t v) {
+  v &= 0x1fffffull;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
 int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const int32_t* conn, const double* xyz,
-                int rank, int nranks, int partitioner, int pairs_per_cta, std::string& err) {
+                int rank, int nranks, int partitioner, int pairs_per_cta, int node_order, std::string& err) {
   const int nen = elem_type == RDC_TET4 ? 4 : 8;
   S.nen = nen; S.nv = nv; S.rank = rank; S.nranks = nranks; S.N_glob = N; S.E_glob = E;
   S.pairs_per_cta = pairs_per_cta;
@@ -148,12 +159,39 @@ int build_setup(HostSetup& S, int elem_type, int nv, int64_t N, int64_t E, const
   if (rc) return rc;
   if (nranks > 1) S.owner_glob = owner;
 
-  // local node set: owned (ascending global id), then ghosts ordered by (owner, global id)
+  // local node set: owned, then ghosts ordered by (owner, global id).  Owned nodes are numbered along a Morton curve of
+  // their coordinates (node_order 1, default): consecutive rows then belong to one small neighbourhood, so the 16 rows of
+  // an SpMV tile and the ~5 nodes of an assembly CTA share most of the x / u entries they gather (L1 reuse) whatever
+  // numbering the mesh generator chose; node_order 0 keeps ascending global ids.  User-facing dof ids are untouched
+  // (d_dofmap translates), and rdc_download_csr sorts by global dof, so the bit-exact pattern comparison is unaffected.
   S.glob2loc.assign((size_t)N, -1);
   S.loc2glob.clear();
   for (int64_t g = 0; g < N; g++)
-    if (owner[g] == rank) { S.glob2loc[g] = (int32_t)S.loc2glob.size(); S.loc2glob.push_back((int32_t)g); }
+    if (owner[g] == rank) S.loc2glob.push_back((int32_t)g);
   S.n_owned = (int32_t)S.loc2glob.size();
+  if (node_order == 1 && S.n_owned > 1) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int32_t g : S.loc2glob)
+      for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], xyz[(int64_t)g * 3 + d]); hi[d] = std::max(hi[d], xyz[(int64_t)g * 3 + d]); }
+    double inv[3];
+    for (int d = 0; d < 3; d++) inv[d] = hi[d] > lo[d] ? 2097151.0 / (hi[d] - lo[d]) : 0.0;
+    std::vector<std::pair<uint64_t, int32_t>> key((size_t)S.n_owned);
+#pragma omp parallel for schedule(static)
+    for (int32_t k = 0; k < S.n_owned; k++) {
+      const int32_t g = S.loc2glob[k];
+      uint64_t m = 0;
+      for (int d = 0; d < 3; d++) {
+        double q = (xyz[(int64_t)g * 3 + d] - lo[d]) * inv[d];
+        if (!(q >= 0.0)) q = 0.0;
+        if (q > 2097151.0) q = 2097151.0;
+        m |= spread21((uint64_t)q) << d;
+      }
+      key[k] = std::make_pair(m, g);
+    }
+    std::sort(key.begin(), key.end());   // ties (coincident quantised points) by global id: deterministic
+    for (int32_t k = 0; k < S.n_owned; k++) S.loc2glob[k] = key[k].second;
+  }
+  for (int32_t k = 0; k < S.n_owned; k++) S.glob2loc[S.loc2glob[k]] = k;
   // local elements = elements with at least one owned node
   S.elem_glob.clear();
   std::vector<int32_t> ghosts;

@@ -808,11 +808,28 @@ __global__ void __launch_bounds__(RED_THREADS) k_ripf_check(int n_owned, int n_l
 }
 
 // ------------------------------------------------------------------- user vector gather / scatter
-__global__ void k_gather(size_t n, const int32_t* __restrict__ map, const double* __restrict__ src, double* __restrict__ dst) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[map[i]];
+// Thread t handles dof (node_by_glob[t / nv], t % nv): consecutive threads touch ascending GLOBAL dofs, i.e. the user
+// vector (possibly pinned host memory read or written over PCIe) is walked in order whatever the local numbering is.
+// n_nodes_used: all local nodes (gather) or a prefix test on owned nodes (scatter writes owned dofs only).
+__global__ void k_gather(size_t n, int nv, int n_owned_limit, const int32_t* __restrict__ node_by_glob, const int32_t* __restrict__ map,
+                         const double* __restrict__ src, double* __restrict__ dst) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = t / nv;
+    const int node = node_by_glob[k];
+    if (node >= n_owned_limit) continue;
+    const size_t i = (size_t)node * nv + (t - k * nv);
+    dst[i] = src[map[i]];
+  }
 }
-__global__ void k_scatter(size_t n, const int32_t* __restrict__ map, const double* __restrict__ src, double* __restrict__ dst) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[map[i]] = src[i];
+__global__ void k_scatter(size_t n, int nv, int n_owned_limit, const int32_t* __restrict__ node_by_glob, const int32_t* __restrict__ map,
+                          const double* __restrict__ src, double* __restrict__ dst) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = t / nv;
+    const int node = node_by_glob[k];
+    if (node >= n_owned_limit) continue;
+    const size_t i = (size_t)node * nv + (t - k * nv);
+    dst[map[i]] = src[i];
+  }
 }
 // pack nv values of each listed node
 __global__ void k_pack(size_t n_nodes, int nv, const int32_t* __restrict__ idx, const double* __restrict__ x, double* __restrict__ buf) {
@@ -831,14 +848,14 @@ static inline unsigned grid_for(size_t n) {
 
 int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc) {
   const size_t n = (size_t)c->S.n_loc * c->nv;
-  k_gather<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_dofmap, src_glob, dst_loc);
+  k_gather<<<grid_for(n), 256, 0, c->stream>>>(n, c->nv, c->S.n_loc, c->d_node_by_glob, c->d_dofmap, src_glob, dst_loc);
   c->st.kernel_launches++;
   RDC_CUDA(cudaGetLastError());
   return 0;
 }
 int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob) {
-  const size_t n = (size_t)c->S.n_owned * c->nv;
-  k_scatter<<<grid_for(n), 256, 0, c->stream>>>(n, c->d_dofmap, src_loc, dst_glob);
+  const size_t n = (size_t)c->S.n_loc * c->nv;   // walks all local nodes in global order, writes the owned ones
+  k_scatter<<<grid_for(n), 256, 0, c->stream>>>(n, c->nv, c->S.n_owned, c->d_node_by_glob, c->d_dofmap, src_loc, dst_glob);
   c->st.kernel_launches++;
   RDC_CUDA(cudaGetLastError());
   return 0;
