@@ -227,6 +227,8 @@ int rdc_region_last_mean(rdc_ctx*, int var, double* mean /* [n_regions] */);
 /* read-only streaming probe over the stored operator values (reference point for the SpMV roofline): mean ms, bytes */
 int rdc_bench_stream(rdc_ctx*, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes);
 
+/* measured rate of the fp64 pipe (independent DFMA chains, full occupancy), TFLOP/s: the compute roofline of the assembly kernel */
+int rdc_bench_dfma(rdc_ctx*, double* tflops);
 /* cost of one grid barrier (mode 0) / reduction-barrier (mode 1) of the persistent Krylov kernel on this device: mean us */
 int rdc_bench_barrier(rdc_ctx*, int reps, int ctas_per_sm, int mode, double* mean_us);
 
@@ -262,6 +264,7 @@ struct rdc_stats {
   /* distributed runs: 1 when ghost values and dot products travel over NVLink peer memory (cudaIpc arenas), 0 on the
    * NCCL transport; p2p_fused = the exchanges are finished inside the producing Krylov kernels */
   int     p2p_on, p2p_fused;
+  int     bicg_persistent;  /* the last BiCGStab solve ran as one cooperative launch (its SpMV time is then measured with %globaltimer in the kernel) */
 };
 int rdc_get_stats(rdc_ctx*, struct rdc_stats*);
 /* Host-only probe of the node partition and halo lists of rank `rank` (no device needed; used by the CPU
@@ -273,8 +276,9 @@ int rdc_probe_partition(int elem_type, int nvars, int64_t n_nodes, int64_t n_ele
                         int32_t** send_ptr, int32_t** send_glob, int32_t** recv_ptr, int32_t** recv_glob);
 /* Tuning switch of the context (defaults: environment RDC_<NAME>): "spmv_tma" 1/0 (TMA-staged or LDG SpMV),
  * "spmv_minb", "spmv_ctas_per_sm", "tma_ctas_per_sm", "tma_stages", "sync_every", "p2p_fused_ar",
- * "p2p_fused_halo", "bicg_persist" 1/0 (BiCGStab as one cooperative launch with grid barriers, or five launches per
- * iteration), "trace".  Results do not depend on them beyond floating-point summation order. */
+ * "p2p_fused_halo", "bicg_persist" 1/0/-1 (BiCGStab as one cooperative launch with grid barriers, five launches per iteration, or
+ * chosen by the problem size per GPU), "node_order" 1/0 (read at rdc_create from RDC_NODE_ORDER: owned nodes numbered along a
+ * Morton curve or by ascending global id), "trace".  Results do not depend on them beyond floating-point summation order. */
 int rdc_set_option(rdc_ctx*, const char* name, int value);
 /* Host-only probes of set-up logic, for CPU tests (arrays malloc'ed by the library, rdc_free): the SpMV tile cutter
  * (tiles = n_tiles x {row0, nrows, first block, nblocks}; n_tiles = -1 when a row exceeds max_blocks) and the region

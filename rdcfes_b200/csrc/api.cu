@@ -648,6 +648,21 @@ extern "C" int rdc_bench_stream(rdc_ctx* c, int reps, int ctas_per_sm, double* m
   return rc;
 }
 
+extern "C" int rdc_bench_dfma(rdc_ctx* c, double* tflops) {
+  CHECK_CTX(c);
+  if (!tflops) return RDC_E_ARG;
+  const int iters = 20000;
+  int rc = launch_dfma_probe(c, 1000);  // warm-up
+  cudaEventRecord(c->ev0, c->stream);
+  if (!rc) rc = launch_dfma_probe(c, iters);
+  cudaEventRecord(c->ev1, c->stream);
+  cudaEventSynchronize(c->ev1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  *tflops = 2.0 * 8.0 * iters * (148.0 * 8 * 256) / (ms * 1e-3) / 1e12;
+  return rc;
+}
+
 extern "C" int rdc_bench_barrier(rdc_ctx* c, int reps, int ctas_per_sm, int mode, double* mean_us) {
   CHECK_CTX(c);
   if (reps < 1 || !mean_us || ctas_per_sm < 1 || ctas_per_sm > 8) return RDC_E_ARG;

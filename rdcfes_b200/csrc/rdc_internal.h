@@ -105,7 +105,8 @@ struct rdc_options {
   int p2p_fused_ar = 1;        // all-reduce finished inside the producing kernel
   int p2p_fused_halo = 1;      // ghost exchange inside the BiCGStab vector kernels
   int node_order = 1;          // local numbering of the owned nodes: 1 Morton curve of the coordinates, 0 ascending global id (read at rdc_create)
-  int bicg_persist = 1;        // BiCGStab as one cooperative launch (solver.cu k_bicgstab_persist); 0 = five launches per iteration
+  int bicg_persist = -1;       // BiCGStab as one cooperative launch (solver.cu k_bicgstab_persist): 1 always, 0 never (five launches per
+                               // iteration), -1 automatic: when a CTA of the resident grid gets at most 64 operator tiles per SpMV
   int persist_timing = 1;      // the persistent solver times its phases (SpMV time of rdc_stats); 0 = no timer reads
   int trace = 0;               // print the device time of every operation of BiCGStab iteration 4
 };
@@ -190,6 +191,7 @@ int solver_persist_begin(rdc_ctx* c, int pc, double rtol, int maxits);   // 1: n
 int solver_persist_end(rdc_ctx* c, int* its, double* res);
 int launch_stream_probe(rdc_ctx* c, int ctas_per_sm);
 int launch_barrier_probe(rdc_ctx* c, int reps, int ctas_per_sm, int mode);
+int launch_dfma_probe(rdc_ctx* c, int iters);
 int spmv_masks_ok();                // solver.cu's entry masks agree with the model definitions
 int launch_gather(rdc_ctx* c, const double* src_glob, double* dst_loc);     // dst_loc[l] = src[dofmap[l]]
 int launch_scatter(rdc_ctx* c, const double* src_loc, double* dst_glob);    // owned part only

@@ -1383,6 +1383,7 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
   // r = r0 = B (b - A x), <r,r>, ||B b||^2 in one pass over the operator
   if ((rc = refresh_u_ghosts(c))) return rc;
   bool fused;
+  c->st.bicg_persistent = 0;
   {
     const ArCtx ar = ar_begin(c, &fused);
     if ((rc = spmv(c, SPMV_RESID, c->d_u, r, scale, c->d_rhs, r0, D + D_INIT, false, false, ar))) return rc;
@@ -2025,6 +2026,17 @@ void p2p_fill_halo_args_parity(rdc_ctx* c, HaloArgs* A, int par);
 
 // BiCGStab as ONE cooperative launch (see k_bicgstab_persist).  Needs the TMA tiles; distributed runs need the peer-memory
 // transport (the exchanges happen inside the kernel).  Returns 1 when the caller has to use the five-launch version.
+// Which BiCGStab runs.  Measured on B200 (tools/iter_probe.py, ADPM): at 1.3 M tets per GPU (the per-rank size of an 8-GPU
+// run of the 10 M-tet mesh, 16 tiles per CTA) the persistent kernel needs 132 us per iteration against 145 us, and it
+// stops in the iteration that converges instead of a few queued launches later; at 10 M tets on one GPU (122 tiles per
+// CTA) its SpMV phases run 7 % below the stand-alone kernel and the five-launch version wins (774 vs 821 us).
+static bool want_persistent(const rdc_ctx* c) {
+  if (c->opt.bicg_persist >= 0) return c->opt.bicg_persist != 0;
+  const SolverWork* W = c->work;
+  const int grid = 148 * (c->nv == 3 ? 6 : 2);
+  return W->n_tiles <= 64 * grid;
+}
+
 static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, int maxits) {
   SolverWork* W = c->work;
   if (!(W->n_tiles > 0 && c->opt.spmv_tma)) return 1;
@@ -2074,6 +2086,7 @@ static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, 
   if (rc) return rc;
   c->u_ghost_fresh = false;
   W->persist_pending = true;
+  c->st.bicg_persistent = 1;
   return 0;
 }
 
@@ -2112,7 +2125,7 @@ static int bicgstab_persist_end(rdc_ctx* c, int* its_out, double* res_out) {
 
 // the two halves for rdc_step (api.cu): between them the caller may queue work that does not need the host (the clamp)
 int solver_persist_begin(rdc_ctx* c, int pc, double rtol, int maxits) {
-  if (!c->opt.bicg_persist || (pc != RDC_PC_JACOBI && pc != RDC_PC_NONE) || maxits < 0) return 1;
+  if (!want_persistent(c) || (pc != RDC_PC_JACOBI && pc != RDC_PC_NONE) || maxits < 0) return 1;
   c->work->n_ev_used = 0;
   return bicgstab_persist_begin(c, pc == RDC_PC_JACOBI ? c->d_dinv : nullptr, rtol, maxits);
 }
@@ -2137,7 +2150,7 @@ int solver_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, int resta
   else if (ksp == RDC_KSP_CG) rc = pcg(c, scale, rtol, maxits, its, res);
   else if (ksp == RDC_KSP_BICGSTAB) {
     rc = 1;
-    if (c->opt.bicg_persist) {
+    if (want_persistent(c)) {
       rc = bicgstab_persist_begin(c, scale, rtol, maxits);
       persistent = rc != 1;
       if (rc == 0) rc = bicgstab_persist_end(c, its, res);
@@ -2194,6 +2207,30 @@ int launch_barrier_probe(rdc_ctx* c, int reps, int ctas_per_sm, int mode) {
   RDC_CUDA(cudaLaunchCooperativeKernel((void*)k_barrier_probe, dim3(148u * ctas_per_sm), dim3(RED_THREADS), args, 0, c->stream));
   RDC_CUDA(cudaMemsetAsync(W->flag, 0, 2 * sizeof(unsigned), c->stream));   // the solver expects cleared epoch flags
   c->st.kernel_launches++;
+  return 0;
+}
+
+// fp64 pipe probe: 8 independent DFMA chains per thread, full occupancy -- the rate the assembly kernel's arithmetic is
+// measured against (its roofline is the fp64 pipe and the issue slots, not HBM)
+__global__ void __launch_bounds__(256) k_dfma_probe(int iters, double seed, double* out) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = seed + k + threadIdx.x * 1e-3;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = fma(a[k], m, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k];
+  if (s == 12345.678) out[0] = s;   // never true: keeps the chains alive
+}
+int launch_dfma_probe(rdc_ctx* c, int iters) {
+  SolverWork* W = c->work;
+  k_dfma_probe<<<148 * 8, 256, 0, c->stream>>>(iters, 1.0, W->h + 900);
+  c->st.kernel_launches++;
+  RDC_CUDA(cudaGetLastError());
   return 0;
 }
 

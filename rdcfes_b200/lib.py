@@ -29,14 +29,14 @@ class Stats(C.Structure):
                 ("bytes_index", C.c_int64), ("kernel_launches", C.c_int64), ("ripf_rt_total_max", C.c_int),
                 ("sum_ms_assemble", C.c_double), ("sum_ms_solve", C.c_double), ("sum_ms_clamp", C.c_double),
                 ("sum_ms_spmv", C.c_double), ("sum_iterations", C.c_int64), ("sum_n_spmv", C.c_int64),
-                ("n_solves", C.c_int64), ("p2p_on", C.c_int), ("p2p_fused", C.c_int)]
+                ("n_solves", C.c_int64), ("p2p_on", C.c_int), ("p2p_fused", C.c_int), ("bicg_persistent", C.c_int)]
 
 
 EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_distributed", "rdc_comm_unique_id",
            "rdc_destroy", "rdc_last_error", "rdc_set_params", "rdc_set_elem_field", "rdc_set_nodal_field",
            "rdc_update_coords", "rdc_set_solution", "rdc_get_solution", "rdc_get_solution_owned", "rdc_get_old_solution", "rdc_get_rhs", "rdc_n_dofs",
            "rdc_set_time", "rdc_set_dt", "rdc_rotate", "rdc_assemble", "rdc_solve", "rdc_clamp", "rdc_step",
-           "rdc_spmv", "rdc_bench_spmv", "rdc_bench_stream", "rdc_bench_barrier", "rdc_download_csr", "rdc_free", "rdc_get_stats", "rdc_set_stream",
+           "rdc_spmv", "rdc_bench_spmv", "rdc_bench_stream", "rdc_bench_barrier", "rdc_bench_dfma", "rdc_download_csr", "rdc_free", "rdc_get_stats", "rdc_set_stream",
            "rdc_version", "rdc_probe_partition", "rdc_set_option", "rdc_set_subdomains", "rdc_region_volumes",
            "rdc_region_last_mean", "rdc_probe_spmv_tiles", "rdc_probe_region_chunks"]
 
@@ -80,7 +80,7 @@ def load():
         "rdc_step": [vp, f64, f64, i32, i32, f64, i32, i32, C.POINTER(i32), C.POINTER(f64)],
         "rdc_spmv": [vp, vp, vp], "rdc_bench_spmv": [vp, i32, C.POINTER(f64)],
         "rdc_bench_stream": [vp, i32, i32, C.POINTER(f64), C.POINTER(i64)],
-        "rdc_bench_barrier": [vp, i32, i32, i32, C.POINTER(f64)],
+        "rdc_bench_barrier": [vp, i32, i32, i32, C.POINTER(f64)], "rdc_bench_dfma": [vp, C.POINTER(f64)],
         "rdc_download_csr": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                              C.POINTER(vp), C.POINTER(vp)],
         "rdc_get_stats": [vp, C.POINTER(Stats)], "rdc_set_stream": [vp, vp], "rdc_set_option": [vp, C.c_char_p, i32], "rdc_set_subdomains": [vp, vp, i32],

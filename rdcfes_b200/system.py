@@ -204,6 +204,12 @@ class TransientRdcSystem:
         self._check(self._L.rdc_bench_spmv(self._h, reps, C.byref(ms)))
         return ms.value
 
+    def bench_dfma(self):
+        """measured fp64-pipe rate of this GPU, TFLOP/s"""
+        t = C.c_double()
+        self._check(self._L.rdc_bench_dfma(self._h, C.byref(t)))
+        return t.value
+
     def bench_stream(self, reps=20, ctas_per_sm=8):
         """(mean ms, bytes) of a read-only pass over the stored operator values."""
         ms, nb = C.c_double(), C.c_int64()
