@@ -1,8 +1,11 @@
 // rdc_libmesh_adapter.h -- the reference-side glue: rdcFEs' libMesh callbacks on top of the C ABI (include/rdc.h).
 //
-// NOT compiled or tested in this repository: it needs libMesh (+ PETSc, MPI), which cannot be installed in the build
-// container.  It is the code a maintainer of InSilicoModellingGroup/rdcFEs drops into src/ and
-// includes from adpm.C / pihna.C / ripf.C / proteas.C / coupled_hcc.C; INTEGRATION.md walks through it.  Everything
+// libMesh (+ PETSc, MPI) cannot be installed in the build container, so this header is compiled and RUN against the serial
+// stand-in oracle/ref_shim/libmesh (libMesh's class and member names; the reference's own model files compile against it
+// unchanged): tests/test_adapter.py builds tests/adapter/adapter_check.cpp, which drives the patched time loop of
+// adpm.C:60-84 through this adapter for all five models on a GPU and compares with the oracle.  Against the real libMesh it
+// has not been built.  It is the code a maintainer of InSilicoModellingGroup/rdcFEs drops into src/ and includes from
+// adpm.C / pihna.C / ripf.C / proteas.C / coupled_hcc.C; INTEGRATION.md walks through it.  Everything
 // numerical happens behind rdc.h; this file only flattens libMesh objects once and forwards the per-step calls:
 //
 //   assemble_<m>(es, name)      -> RdcAdapter::assemble()        (adpm.C:324, pihna.C:318, ripf.C:337, proteas.C:338, coupled_hcc.C:414)
@@ -159,9 +162,17 @@ class RdcAdapter {
 
 // installed with  model.linear_solver.reset(new RdcLinearSolver(init.comm(), adapter))  after es.init();
 // LinearImplicitSystem::solve() then calls assemble() (our callback) and this solve() instead of PETSc's KSP
+// "rdc/ksp" in es.parameters: "bicgstab" (default), "gmres" (libMesh's own default, GMRES(30)) or "cg"
+inline int rdc_ksp_from_parameters(const libMesh::EquationSystems& es) {
+  if (!es.parameters.have_parameter<std::string>("rdc/ksp")) return RDC_KSP_BICGSTAB;
+  const std::string k = es.parameters.get<std::string>("rdc/ksp");
+  return k == "gmres" ? RDC_KSP_GMRES : (k == "cg" ? RDC_KSP_CG : RDC_KSP_BICGSTAB);
+}
+
 class RdcLinearSolver : public libMesh::LinearSolver<libMesh::Number> {
  public:
-  RdcLinearSolver(const libMesh::Parallel::Communicator& comm, RdcAdapter& a, int ksp = RDC_KSP_GMRES)
+  // ksp: pass rdc_ksp_from_parameters(es) -- BiCGStab (the benchmarked method) unless es.parameters "rdc/ksp" says otherwise
+  RdcLinearSolver(const libMesh::Parallel::Communicator& comm, RdcAdapter& a, int ksp = RDC_KSP_BICGSTAB)
       : libMesh::LinearSolver<libMesh::Number>(comm), a_(a), ksp_(ksp) {}
   void init(const char* = nullptr) override { this->_is_initialized = true; }
   void clear() override { this->_is_initialized = false; }

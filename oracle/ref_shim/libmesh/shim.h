@@ -23,6 +23,7 @@
 #include <map>
 #include <memory>
 #include <numeric>
+#include <optional>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -40,7 +41,7 @@
 #define libmesh_assert_not_equal_to(a, b) ((void)0)
 #define libmesh_dbg_var(x)
 #define libmesh_error() throw std::runtime_error(std::string("libmesh_error at ") + __FILE__ + ":" + std::to_string(__LINE__))
-#define libmesh_error_msg(m) libmesh_error()
+#define libmesh_error_msg(m) throw std::runtime_error(std::string("libmesh_error: ") + std::string(m))
 #define libmesh_not_implemented() libmesh_error()
 #define libmesh_make_unique std::make_unique
 #define libmesh_nullptr nullptr
@@ -802,10 +803,30 @@ class ImplicitSystem : public ExplicitSystem {
   const SparseMatrix<Number>& get_system_matrix() const { return *matrix; }
   SparseMatrix<Number>& get_matrix(const std::string&) { return *matrix; }
 };
+enum LinearConvergenceReason { CONVERGED_RTOL_NORMAL = 1, CONVERGED_ATOL_NORMAL = 9, CONVERGED_RTOL = 2, CONVERGED_ATOL = 3, CONVERGED_ITS = 4,
+                               CONVERGED_ITERATING = 0, DIVERGED_NULL = -2, DIVERGED_ITS = -3, DIVERGED_DTOL = -4, DIVERGED_BREAKDOWN = -5,
+                               DIVERGED_NAN = -9, UNKNOWN_FLAG = -128 };
+template <class T> class ShellMatrix {};
+// [upstream] libMesh::LinearSolver<T>: the pure virtuals a subclass has to provide (signatures of libMesh @d3bda6c)
 template <class T> class LinearSolver {
  public:
+  LinearSolver(const Parallel::Communicator&) {}
   virtual ~LinearSolver() {}
-  virtual std::pair<unsigned, Real> solve(SparseMatrix<T>&, NumericVector<T>&, NumericVector<T>&, const double, const unsigned) { return {0u, 0.0}; }
+  virtual void init(const char* name = nullptr) = 0;
+  virtual void clear() {}
+  bool initialized() const { return _is_initialized; }
+  virtual std::pair<unsigned int, Real> solve(SparseMatrix<T>&, SparseMatrix<T>&, NumericVector<T>&, NumericVector<T>&,
+                                              const std::optional<double> tol = std::nullopt,
+                                              const std::optional<unsigned int> m_its = std::nullopt) = 0;
+  virtual std::pair<unsigned int, Real> solve(const ShellMatrix<T>&, NumericVector<T>&, NumericVector<T>&, const std::optional<double> = std::nullopt,
+                                              const std::optional<unsigned int> = std::nullopt) = 0;
+  virtual std::pair<unsigned int, Real> solve(const ShellMatrix<T>&, const SparseMatrix<T>&, NumericVector<T>&, NumericVector<T>&,
+                                              const std::optional<double> = std::nullopt, const std::optional<unsigned int> = std::nullopt) = 0;
+  virtual void print_converged_reason() const {}
+  virtual LinearConvergenceReason get_converged_reason() const = 0;
+
+ protected:
+  bool _is_initialized = false;
 };
 class LinearImplicitSystem : public ImplicitSystem {
  public:
@@ -818,7 +839,7 @@ class LinearImplicitSystem : public ImplicitSystem {
   void solve() override {
     matrix->zero(); rhs->zero();
     assemble();
-    if (linear_solver) { auto r = linear_solver->solve(*matrix, *solution, *rhs, 1e-12, 5000); n_its = r.first; final_res = r.second; }
+    if (linear_solver) { auto r = linear_solver->solve(*matrix, *matrix, *solution, *rhs, 1e-12, 5000u); n_its = r.first; final_res = r.second; }
     update();
   }
   unsigned n_linear_iterations() const { return n_its; }

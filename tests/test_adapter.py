@@ -1,0 +1,72 @@
+"""adapter/rdc_libmesh_adapter.h -- the reference-side glue of INTEGRATION.md -- compiled and run.
+
+libMesh cannot be installed here, so the adapter is built against the serial stand-in oracle/ref_shim/libmesh (the
+interface the reference's own model files compile against unchanged).  CPU: it compiles and links against
+librdcgpu.so.  GPU: tests/adapter/adapter_check.cpp runs the patched time loop of adpm.C:60-84 (assemble callback ->
+RdcAdapter::assemble, RdcLinearSolver on model.linear_solver, rotate / check_solution / pull_solution) for every model
+and the result is compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from rdcfes_b200 import build as B
+from rdcfes_b200 import params as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+EXE = os.path.join(HERE, "adapter", "adapter_check")
+
+
+def build_adapter_check():
+    so = B.build()
+    src = os.path.join(HERE, "adapter", "adapter_check.cpp")
+    deps = [src, os.path.join(ROOT, "adapter", "rdc_libmesh_adapter.h"), os.path.join(ROOT, "oracle", "ref_shim", "libmesh", "shim.h"), so]
+    if os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(d) for d in deps):
+        return EXE
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "oracle", "ref_shim"), "-o", EXE, src,
+                           "-L", os.path.dirname(so), "-lrdcgpu", "-Wl,-rpath," + os.path.dirname(so)])
+    return EXE
+
+
+def test_adapter_compiles_against_the_libmesh_interface():
+    assert os.path.exists(build_adapter_check())
+
+
+def _write_input(path, model, conn, xyz, p, u0, ef, nf, dt, nsteps, ksp):
+    table = P.TABLES[model]
+    with open(path, "w") as f:
+        N, E = xyz.shape[0], conn.shape[0]
+        f.write(f"{model} {conn.shape[1]} {N} {E} {dt!r} {nsteps} {ksp} {len(table)} {0 if ef is None else 3} {0 if nf is None else 2}\n")
+        for (key, _), v in zip(table, p):
+            kind = "int" if key in ("RT_dose/broad/fractions", "RT_dose/focus/fractions") else "real"
+            f.write(f"{key} {kind} {float(v)!r}\n")
+        for arr in (xyz, conn, np.asarray(u0).reshape(-1)) + (() if ef is None else (np.asarray(ef).reshape(-1),)) + \
+                (() if nf is None else (np.asarray(nf).reshape(-1),)):
+            np.savetxt(f, np.asarray(arr).reshape(1, -1), fmt="%d" if np.asarray(arr).dtype.kind == "i" else "%.17g")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ksp", ["bicgstab", "gmres"])
+@pytest.mark.parametrize("model", range(5))
+def test_adapter_runs_the_patched_time_loop(model, ksp, tmp_path):
+    from oracle import oracle as O
+    exe = build_adapter_check()
+    conn, xyz = cases.mesh(cases.TET4, 5, distort=0.2, length=50.0 if model == cases.RIPF else 1.0)
+    p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+    if model == cases.PIHNA and ksp == "gmres":
+        pytest.skip("covered by the BiCGStab run")
+    dt, nsteps = cases.DT[model], 3
+    inp, out = tmp_path / "in.txt", tmp_path / "out.txt"
+    _write_input(inp, model, conn, xyz, p, u0, ef, nf, dt, nsteps, ksp)
+    res = subprocess.run([exe, str(inp), str(out)], capture_output=True, text=True, timeout=300)
+    print(res.stdout, res.stderr[-2000:])
+    assert res.returncode == 0
+    u = np.loadtxt(out)
+    orc = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf)
+    for _ in range(nsteps):
+        orc.step(dt, pc=O.PC_ILU)
+    assert np.linalg.norm(u - orc.u) <= 1e-8 * np.linalg.norm(orc.u)
