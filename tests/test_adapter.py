@@ -69,4 +69,8 @@ def test_adapter_runs_the_patched_time_loop(model, ksp, tmp_path):
     orc = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf)
     for _ in range(nsteps):
         orc.step(dt, pc=O.PC_ILU)
-    assert np.linalg.norm(u - orc.u) <= 1e-8 * np.linalg.norm(orc.u)
+    # north_star: species after N steps within 1e-6; 1e-8 holds for every model but RIPF, whose source terms switch on the
+    # sign of a time derivative that is round-off noise where nothing changes (ripf.C:491-496) -- two converged Krylov
+    # solvers may take different branches there from the second step on
+    tol = 1e-6 if model == cases.RIPF else 1e-8
+    assert np.linalg.norm(u - orc.u) <= tol * np.linalg.norm(orc.u)
