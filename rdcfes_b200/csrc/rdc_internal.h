@@ -106,7 +106,7 @@ struct rdc_options {
   int p2p_fused_halo = 1;      // ghost exchange inside the BiCGStab vector kernels
   int node_order = 1;          // local numbering of the owned nodes: 1 Morton curve of the coordinates, 0 ascending global id (read at rdc_create)
   int bicg_persist = -1;       // BiCGStab as one cooperative launch (solver.cu k_bicgstab_persist): 1 always, 0 never (five launches per
-                               // iteration), -1 automatic: when a CTA of the resident grid gets at most 64 operator tiles per SpMV
+                               // iteration), -1 automatic: when a CTA of the resident grid gets at most 40 operator tiles per SpMV
   int persist_timing = 1;      // the persistent solver times its phases (SpMV time of rdc_stats); 0 = no timer reads
   int trace = 0;               // print the device time of every operation of BiCGStab iteration 4
 };

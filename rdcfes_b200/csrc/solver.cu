@@ -2026,15 +2026,16 @@ void p2p_fill_halo_args_parity(rdc_ctx* c, HaloArgs* A, int par);
 
 // BiCGStab as ONE cooperative launch (see k_bicgstab_persist).  Needs the TMA tiles; distributed runs need the peer-memory
 // transport (the exchanges happen inside the kernel).  Returns 1 when the caller has to use the five-launch version.
-// Which BiCGStab runs.  Measured on B200 (tools/iter_probe.py, ADPM): at 1.3 M tets per GPU (the per-rank size of an 8-GPU
-// run of the 10 M-tet mesh, 16 tiles per CTA) the persistent kernel needs 132 us per iteration against 145 us, and it
-// stops in the iteration that converges instead of a few queued launches later; at 10 M tets on one GPU (122 tiles per
-// CTA) its SpMV phases run 7 % below the stand-alone kernel and the five-launch version wins (774 vs 821 us).
+// Which BiCGStab runs.  Measured on B200 (tools/iter_probe.py, ADPM, us per iteration persistent / five-launch): 1.3 M tets
+// per GPU (the per-rank size of an 8-GPU run of the 10 M-tet mesh, 16 operator tiles per CTA and SpMV) 132 / 145; 2.5 M tets
+// (31 tiles) 225 / 225; 5.1 M tets (62 tiles) 420 / 401; 10.1 M tets (122 tiles) 821 / 774 -- the SpMV phases of the
+// cooperative kernel run ~6 % below the stand-alone kernel, its barriers cost less than launches only when the phases are
+// short.  The persistent kernel also stops in the iteration that converges instead of a few queued launches later.
 static bool want_persistent(const rdc_ctx* c) {
   if (c->opt.bicg_persist >= 0) return c->opt.bicg_persist != 0;
   const SolverWork* W = c->work;
   const int grid = 148 * (c->nv == 3 ? 6 : 2);
-  return W->n_tiles <= 64 * grid;
+  return W->n_tiles <= 40 * grid;
 }
 
 static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, int maxits) {
