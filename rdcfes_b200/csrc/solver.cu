@@ -56,6 +56,7 @@ struct SolverWork {
   int* h_ring = nullptr;     // pinned copies of the convergence flag
   int4* tiles = nullptr;     // SpMV tiles {row0, nrows, first block, nblocks} (k_spmv_tma)
   int n_tiles = 0;
+  int tiles_uniform = 0;                // number of rows when every tile but the last has exactly SPMV_TILE_ROWS rows, else 0
   unsigned* flag = nullptr;             // epoch flag of the persistent solver's grid barriers
   unsigned long long* t_spmv = nullptr; // [8] phase timers of the last persistent solve (see PersistArgs)
   double persist_phase_ms[4] = {0, 0, 0, 0};
@@ -341,12 +342,13 @@ struct SpmvStage {
   static constexpr int VAL_BYTES = ((SPMV_CAPB * NKV + 2) * 8 + 15) / 16 * 16;
   static constexpr int COL_BYTES = ((SPMV_CAPB + 4) * 4 + 15) / 16 * 16;
   static constexpr int RP_BYTES = ((SPMV_TILE_ROWS + 1 + 4) * 4 + 15) / 16 * 16;
-  static constexpr int BYTES = (VAL_BYTES + COL_BYTES + RP_BYTES + 127) / 128 * 128;
+  static constexpr int DESC_OFF = VAL_BYTES + COL_BYTES + RP_BYTES;   // the tile's own descriptor {row0, nrows, b0, nblk}
+  static constexpr int BYTES = (DESC_OFF + 16 + 127) / 128 * 128;
 };
 
 template <int NV, unsigned KMASK, int MODE, int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
-k_spmv_tma(int n_tiles, const int4* __restrict__ tiles, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+k_spmv_tma(int n_tiles, int uniform16, const int4* __restrict__ tiles, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
            const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ rowscale, const double* __restrict__ w, double* __restrict__ y2, double* partial,
            unsigned* counter, double* out, const int* __restrict__ done, const ArCtx ar) {
@@ -364,45 +366,63 @@ k_spmv_tma(int n_tiles, const int4* __restrict__ tiles, const int32_t* __restric
   }
   __syncthreads();
 
-  // producer side (thread 0): three bulk copies per tile, sources aligned down to 16 B
-  auto issue = [&](int tile, int stage) {
-    const int4 t = tiles[tile];                       // {row0, nrows, b0, nblk}
+  // producer side (thread 0): four bulk copies per tile -- operator values, column ids, row pointers (sources aligned
+  // down to 16 B) and the 16-byte tile descriptor itself, so that the 255 consumer threads never load a descriptor from
+  // global memory (that load, re-issued by every warp in every iteration, drew 17-25 % of the kernel's stall samples);
+  // the producer keeps its own descriptors two tiles ahead in registers
+  auto issue = [&](int tile, int stage, const int4 t) {
     const int skip_v = (int)(((long long)t.z * NKV) & 1), skip_c = t.z & 3, skip_r = t.x & 3;
     const unsigned vb = (unsigned)(((skip_v + t.w * NKV) * 8 + 15) & ~15);
     const unsigned cb = (unsigned)(((skip_c + t.w) * 4 + 15) & ~15);
     const unsigned rb = (unsigned)(((skip_r + t.y + 1) * 4 + 15) & ~15);
     unsigned char* base = s_raw + (size_t)stage * ST::BYTES;
     const unsigned bar = smem_u32(&s_bar[stage]);
-    mbar_expect_tx(bar, vb + cb + rb);
+    mbar_expect_tx(bar, vb + cb + rb + 16u);
     bulk_g2s(smem_u32(base), val + ((long long)t.z * NKV - skip_v), vb, bar);
     bulk_g2s(smem_u32(base + ST::VAL_BYTES), col + (t.z - skip_c), cb, bar);
     bulk_g2s(smem_u32(base + ST::VAL_BYTES + ST::COL_BYTES), rowptr + (t.x - skip_r), rb, bar);
+    bulk_g2s(smem_u32(base + ST::DESC_OFF), tiles + tile, 16u, bar);
   };
   const int first = (int)blockIdx.x, tstride = (int)gridDim.x;
+  int4 pn = make_int4(0, 0, 0, 0);   // producer: descriptor of the next tile to issue, fetched one iteration ahead
   if (tid == 0) {
     for (int s = 0; s < STAGES - 1; s++)
-      if (first + s * tstride < n_tiles) issue(first + s * tstride, s);
+      if (first + s * tstride < n_tiles) issue(first + s * tstride, s, tiles[first + s * tstride]);
+    if (first + (STAGES - 1) * tstride < n_tiles) pn = tiles[first + (STAGES - 1) * tstride];
   }
   double d[2] = {0.0, 0.0};
-  int4 tn = first < n_tiles ? tiles[first] : make_int4(0, 0, 0, 0);
 #pragma unroll 1
   for (int i = 0, tile = first; tile < n_tiles; i++, tile += tstride) {
     const int stage = i % STAGES;
-    const int4 t = tn;
-    if (tile + tstride < n_tiles) tn = tiles[tile + tstride];
     // refill the stage that was consumed in the previous iteration (every thread has passed its barrier)
-    if (tid == 0 && tile + (STAGES - 1) * tstride < n_tiles) issue(tile + (STAGES - 1) * tstride, (i + STAGES - 1) % STAGES);
-    // epilogue operands do not depend on the tile data: fetch them while the tile is (possibly) still landing
+    if (tid == 0) {
+      const int nt = tile + (STAGES - 1) * tstride;
+      if (nt < n_tiles) issue(nt, (i + STAGES - 1) % STAGES, pn);
+      if (nt + tstride < n_tiles) pn = tiles[nt + tstride];
+    }
+    // epilogue operands do not depend on the tile data.  When every tile has exactly SPMV_TILE_ROWS rows (regular
+    // meshes; flag from the host) the row is known without the descriptor and they are fetched while the tile is still
+    // landing; otherwise right after the descriptor arrived, in flight during the x gather
+    double sc = 1.0, wv = 0.0;
+    if (uniform16) {   // carries the number of rows when set
+      const int row = tile * SPMV_TILE_ROWS + hw;
+      if (row < uniform16 && lane < NV) {
+        const size_t o = (size_t)row * NV + lane;
+        if (rowscale) sc = rowscale[o];
+        if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
+        if (MODE == SPMV_DOT_SELF) wv = x[o];
+      }
+    }
+    mbar_wait(smem_u32(&s_bar[stage]), (unsigned)((i / STAGES) & 1));
+    const int4 t = *reinterpret_cast<const int4*>(s_raw + (size_t)stage * ST::BYTES + ST::DESC_OFF);
     const bool live = hw < t.y;
     const int row = t.x + hw;
     const size_t o = (size_t)row * NV + (lane < NV ? lane : 0);
-    double sc = 1.0, wv = 0.0;
-    if (live && lane < NV) {
+    if (!uniform16 && live && lane < NV) {
       if (rowscale) sc = rowscale[o];
       if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
       if (MODE == SPMV_DOT_SELF) wv = x[o];
     }
-    mbar_wait(smem_u32(&s_bar[stage]), (unsigned)((i / STAGES) & 1));
     if (live) {
       const unsigned char* base = s_raw + (size_t)stage * ST::BYTES;
       const double* s_val = reinterpret_cast<const double*>(base) + (((long long)t.z * NKV) & 1);
@@ -517,7 +537,7 @@ int spmv_masks_ok() {
 }
 
 template <int NV, unsigned KMASK, int STAGES>
-static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const int4* tiles, const int32_t* rowptr, const int32_t* col,
+static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, int uniform16, const int4* tiles, const int32_t* rowptr, const int32_t* col,
                     const double* val, const double* x, double* y, const double* rowscale, const double* w, double* y2,
                     double* partial, unsigned* counter, double* out, const int* done, const ArCtx& ar) {
   constexpr int SMEM = STAGES * SpmvStage<popc_c(KMASK)>::BYTES;
@@ -533,7 +553,7 @@ static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, const
     if (e != cudaSuccess) return -1;
     attr_done = true;
   }
-#define RDC_TMA_GO(MODE) k_spmv_tma<NV, KMASK, MODE, STAGES><<<grid, RED_THREADS, SMEM, st>>>(n_tiles, tiles, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
+#define RDC_TMA_GO(MODE) k_spmv_tma<NV, KMASK, MODE, STAGES><<<grid, RED_THREADS, SMEM, st>>>(n_tiles, uniform16, tiles, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
   switch (mode) {
     case SPMV_PLAIN: RDC_TMA_GO(SPMV_PLAIN); break;
     case SPMV_DOT_W: RDC_TMA_GO(SPMV_DOT_W); break;
@@ -577,7 +597,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
     const int per_sm = per_sm_env > 0 ? per_sm_env : (c->nv == 3 ? 6 : 2);  // measured: 2 stages x 6 CTAs/SM beats 3 x 4 by 16 %
     unsigned tg = (unsigned)(W->n_tiles < 148 * per_sm ? W->n_tiles : 148 * per_sm);
     if (tg > (unsigned)SPMV_MAX_GRID) tg = SPMV_MAX_GRID;   // W->partial holds 2 * SPMV_MAX_GRID per-CTA partials
-#define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
+#define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles_uniform, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
     int trc;
     switch (c->model) {
       case RDC_ADPM: trc = stages_env == 3 ? RDC_TMA_MODEL(3, KM_ADPM, 3) : RDC_TMA_MODEL(3, KM_ADPM, 2); break;
@@ -940,6 +960,9 @@ int solver_init(rdc_ctx* c) {
       RDC_CUDA(cudaMemcpyAsync(W->tiles, tl.data(), tl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
       RDC_CUDA(cudaStreamSynchronize(c->stream));
       W->n_tiles = (int)(tl.size() / 4);
+      bool uni = true;
+      for (int k = 0; k + 1 < W->n_tiles && uni; k++) uni = tl[(size_t)4 * k + 1] == SPMV_TILE_ROWS && tl[(size_t)4 * k] == k * SPMV_TILE_ROWS;
+      W->tiles_uniform = uni ? c->S.n_owned : 0;
     }
   }
   RDC_CUDA(cudaMalloc(&W->flag, 2 * sizeof(unsigned)));
@@ -1479,7 +1502,7 @@ struct PersistHalo {
   int on = 0, nv = 1;
 };
 struct PersistArgs {
-  int n_tiles; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val;
+  int n_tiles; int uniform16; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val;
   const double* scale; const double* b;
   size_t n;
   double *x, *r, *r0, *v, *s, *t, *p0, *p1;
@@ -1684,7 +1707,7 @@ __device__ __noinline__ void grid_allreduce(double v0, double v1, int nval, doub
 // budget of the kernel (40 registers at 6 CTAs/SM) for its own loop; inlined, the loop-carried state of the solver was
 // spilled INSIDE the tile loop (800 bytes of spill traffic per thread, +12 % per iteration).
 struct SpmvOp {
-  int n_tiles; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val; const double* scale;
+  int n_tiles; int uniform16; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val; const double* scale;
 };
 struct SpmvRes { double d0, d1; unsigned gi; };
 template <int NV, unsigned KMASK, int MODE>
@@ -1699,38 +1722,52 @@ __device__ __noinline__ SpmvRes persist_spmv(const SpmvOp A, const double* __res
   const int4* __restrict__ tiles = A.tiles;
   const int n_tiles = A.n_tiles;
   double d[2] = {0.0, 0.0};
-  auto issue = [&](int tile, unsigned slot) {
-    const int4 t = tiles[tile];
+  auto issue = [&](int tile, unsigned slot, const int4 t) {
     const int skip_v = (int)(((long long)t.z * NKV) & 1), skip_c = t.z & 3, skip_r = t.x & 3;
     const unsigned vb = (unsigned)(((skip_v + t.w * NKV) * 8 + 15) & ~15);
     const unsigned cb = (unsigned)(((skip_c + t.w) * 4 + 15) & ~15);
     const unsigned rb = (unsigned)(((skip_r + t.y + 1) * 4 + 15) & ~15);
     unsigned char* base = s_raw + (size_t)(slot % STAGES) * ST::BYTES;
     const unsigned bar = smem_u32(&s_bar[slot % STAGES]);
-    mbar_expect_tx(bar, vb + cb + rb);
+    mbar_expect_tx(bar, vb + cb + rb + 16u);
     bulk_g2s(smem_u32(base), A.val + ((long long)t.z * NKV - skip_v), vb, bar);
     bulk_g2s(smem_u32(base + ST::VAL_BYTES), A.col + (t.z - skip_c), cb, bar);
     bulk_g2s(smem_u32(base + ST::VAL_BYTES + ST::COL_BYTES), A.rowptr + (t.x - skip_r), rb, bar);
+    bulk_g2s(smem_u32(base + ST::DESC_OFF), tiles + tile, 16u, bar);   // the consumers read the descriptor from the stage
   };
   const int first = (int)blockIdx.x, tstride = (int)gridDim.x;
-  if (tid == 0 && first < n_tiles) issue(first, gi);
-  int4 tn = first < n_tiles ? tiles[first] : make_int4(0, 0, 0, 0);
+  int4 pn = make_int4(0, 0, 0, 0);
+  if (tid == 0) {
+    if (first < n_tiles) issue(first, gi, tiles[first]);
+    if (first + tstride < n_tiles) pn = tiles[first + tstride];
+  }
 #pragma unroll 1
   for (int tile = first; tile < n_tiles; tile += tstride, gi++) {
     const unsigned stage = gi % STAGES;
-    const int4 t = tn;
-    if (tile + tstride < n_tiles) tn = tiles[tile + tstride];
-    if (tid == 0 && tile + tstride < n_tiles) issue(tile + tstride, gi + 1);
+    if (tid == 0) {
+      if (tile + tstride < n_tiles) issue(tile + tstride, gi + 1, pn);
+      if (tile + 2 * tstride < n_tiles) pn = tiles[tile + 2 * tstride];
+    }
+    double sc = 1.0, wv = 0.0;
+    if (A.uniform16) {   // regular tiles: the epilogue operands are fetched while the tile is still landing (see k_spmv_tma)
+      const int row = tile * SPMV_TILE_ROWS + hw;
+      if (row < A.uniform16 && lane < NV) {
+        const size_t o = (size_t)row * NV + lane;
+        if (A.scale) sc = A.scale[o];
+        if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
+        if (MODE == SPMV_DOT_SELF) wv = x[o];
+      }
+    }
+    mbar_wait(smem_u32(&s_bar[stage]), (unsigned)((gi / STAGES) & 1u));
+    const int4 t = *reinterpret_cast<const int4*>(s_raw + (size_t)stage * ST::BYTES + ST::DESC_OFF);
     const bool live = hw < t.y;
     const int row = t.x + hw;
     const size_t o = (size_t)row * NV + (lane < NV ? lane : 0);
-    double sc = 1.0, wv = 0.0;
-    if (live && lane < NV) {
+    if (!A.uniform16 && live && lane < NV) {
       if (A.scale) sc = A.scale[o];
       if (MODE == SPMV_DOT_W || MODE == SPMV_RESID) wv = w[o];
       if (MODE == SPMV_DOT_SELF) wv = x[o];
     }
-    mbar_wait(smem_u32(&s_bar[stage]), (unsigned)((gi / STAGES) & 1u));
     if (live) {
       const unsigned char* base = s_raw + (size_t)stage * ST::BYTES;
       const double* s_val = reinterpret_cast<const double*>(base) + (((long long)t.z * NKV) & 1);
@@ -1892,7 +1929,7 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
   // r = r0 = B (b - A x), <r,r>, ||B b||^2 (the ghosts of x were exchanged by the host-side launch before)
   unsigned long long t_resid = 0;
   SpmvOp op;
-  op.n_tiles = A.n_tiles; op.tiles = A.tiles; op.rowptr = A.rowptr; op.col = A.col; op.val = A.val; op.scale = A.scale;
+  op.n_tiles = A.n_tiles; op.uniform16 = A.uniform16; op.tiles = A.tiles; op.rowptr = A.rowptr; op.col = A.col; op.val = A.val; op.scale = A.scale;
   {
     const SpmvRes sr = persist_spmv<NV, KMASK, SPMV_RESID>(op, A.x, A.r, A.b, A.r0, s_raw, s_bar, gi);
     gi = sr.gi;
@@ -2047,7 +2084,7 @@ static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, 
   if ((rc = ensure_gmres(c, 1))) return rc;   // borrow V for one more vector
   if ((rc = refresh_u_ghosts(c))) return rc;
   PersistArgs A;
-  A.n_tiles = W->n_tiles; A.tiles = W->tiles; A.rowptr = c->d_rowptr; A.col = c->d_col; A.val = c->d_val;
+  A.n_tiles = W->n_tiles; A.uniform16 = W->tiles_uniform; A.tiles = W->tiles; A.rowptr = c->d_rowptr; A.col = c->d_col; A.val = c->d_val;
   A.scale = scale; A.b = c->d_rhs;
   A.n = (size_t)c->S.n_owned * c->nv;
   A.x = c->d_u; A.r = W->t1; A.r0 = W->t2; A.v = W->t4; A.s = W->hs; A.t = W->V; A.p0 = W->t3; A.p1 = W->hp2;
