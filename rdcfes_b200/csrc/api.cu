@@ -145,7 +145,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     int r;
     if ((r = upload(c, &c->d_conn, S.conn))) return r;
     if ((r = upload(c, &c->d_n2e_ptr, S.n2e_ptr))) return r;
-    if ((r = upload(c, &c->d_pair, S.pair))) return r;
+    if ((r = upload(c, &c->d_pair, S.pair_rec))) return r;
     if ((r = upload(c, &c->d_rowptr, S.rowptr))) return r;
     if ((r = upload(c, &c->d_col, S.col))) return r;
     if ((r = upload(c, &c->d_diag_blk, S.diag_blk))) return r;
@@ -216,13 +216,13 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     const int64_t nkv = c->nkv;
     c->st.bytes_assemble = 4LL * c->nen * El + 24LL * Nl + 8LL * nv * Nl + 8LL * f_e * El + 8LL * f_n * Nl + 8LL * nkv * nnzb + 8LL * nv * No;
     c->st.bytes_spmv = nnzb * (8LL * nkv + 4) + 4LL * (No + 1) + 16LL * nv * No;
-    c->st.bytes_index = 4LL * (int64_t)S.pair.size() + 4LL * (No + 1) * 2 + 48LL * ((int64_t)S.cta_node.size() - 1) + 4LL * (int64_t)S.task.size() +
+    c->st.bytes_index = 4LL * (int64_t)S.pair_rec.size() + 4LL * (No + 1) * 2 + 48LL * ((int64_t)S.cta_node.size() - 1) + 4LL * (int64_t)S.task.size() +
                         2LL * (int64_t)S.clist.size();
     c->st.n_nodes_local = No; c->st.n_nodes_ghost = S.n_ghost; c->st.n_elems_local = El; c->st.nnzb_local = nnzb;
   }
   // the host copies of the big maps are no longer needed
   std::vector<int32_t>().swap(S.pair); std::vector<int32_t>().swap(S.cptr); std::vector<uint16_t>().swap(S.clist);
-  std::vector<int32_t>().swap(S.task);
+  std::vector<int32_t>().swap(S.task); std::vector<int32_t>().swap(S.pair_rec);
   std::vector<int32_t>().swap(S.conn);
   *out = c;
   return RDC_OK;

@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   __shared__ int s_n2e[PAIRS + 1];
   __shared__ int s_diag[PAIRS];
   __shared__ __align__(4) unsigned short s_clist_raw[PAIRS * NEN + 4];  // contributor codes j*PAIRS + pair (offset in a stage slot)
-  __shared__ double s_part[RDC_ASM_MAX_SPLIT * (NKV > 0 ? NKV : 1)];   // partial sums of the pieces of split blocks
 
   const int tid = threadIdx.x;
   // one 48-byte descriptor per CTA: a single load level instead of the chain cta_node -> n2e_ptr -> rowptr -> lists
@@ -170,18 +169,21 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
   }
 
   // ------------------------------------------------------------------ phase 1: one pair per thread
-  if (tid < npairs) {
-    const int pk = A.pair[pair0 + tid];
+  // my pair record: {element << 3 | local index, -, -, -, node ids} at an address known from the block index alone
+  constexpr int REC4 = (NEN + 4) / 4;   // int4 words per record
+  const int4* rec = reinterpret_cast<const int4*>(A.pair) + ((size_t)blockIdx.x * PAIRS + tid) * REC4;
+  const int4 rec0 = __ldg(rec);
+  if (rec0.x >= 0) {
+    const int pk = rec0.x;
     const int e = pk >> 3, li = pk & 7;
     int en[NEN];
-    if constexpr (NEN == 4) {
-      const int4 c4 = reinterpret_cast<const int4*>(A.conn)[e];
+    {
+      const int4 c4 = __ldg(rec + 1);
       en[0] = c4.x; en[1] = c4.y; en[2] = c4.z; en[3] = c4.w;
-    } else {
-      const int4 c4 = reinterpret_cast<const int4*>(A.conn)[2 * (size_t)e];
-      const int4 d4 = reinterpret_cast<const int4*>(A.conn)[2 * (size_t)e + 1];
-      en[0] = c4.x; en[1] = c4.y; en[2] = c4.z; en[3] = c4.w;
-      en[4] = d4.x; en[5] = d4.y; en[6] = d4.z; en[7] = d4.w;
+      if constexpr (NEN == 8) {
+        const int4 d4 = __ldg(rec + 2);
+        en[4] = d4.x; en[5] = d4.y; en[6] = d4.z; en[7] = d4.w;
+      }
     }
     double X[NEN][3], U[NV][NEN], AX[NA_][NEN];
 #pragma unroll
@@ -402,11 +404,14 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
       for (int a = 0; a < NV; a++) A.dinv[(size_t)(node0 + r) * NV + a] = 1.0 / acc[slot_of(KMASK, a * NV + a)];
     }
   };
-  bool any_split = false;
-  for (int t = tid; t < ntask; t += PAIRS) {
-    const int2 tk = t == tid ? my_task : __ldg(A.task + task0 + t);
+  // all lanes of a warp walk the (padded) task list together; the pieces of a split block sit in consecutive lanes of one
+  // warp and their partial sums are added by shuffles in piece order -- no second barrier, no partial sums in memory
+  const int ntask_w = (ntask + 31) & ~31;
+  for (int t = tid; t < ntask_w; t += PAIRS) {
+    int2 tk = make_int2(0, 0);
+    if (t < ntask) tk = t == tid ? my_task : __ldg(A.task + task0 + t);
     const unsigned x = (unsigned)tk.x, y = (unsigned)tk.y;
-    const int c0 = (int)(x >> 16), cnt = (int)(y & 0xffu), np = (int)((y >> 16) & 0xffu);
+    const int c0 = (int)(x >> 16), cnt = (int)(y & 0xffu), piece = (int)((y >> 8) & 0xffu), np = (int)((y >> 16) & 0xffu);
     double acc[NKV > 0 ? NKV : 1];
 #pragma unroll
     for (int s = 0; s < NKV; s++) acc[s] = 0.0;
@@ -415,31 +420,15 @@ __global__ void __launch_bounds__(PAIRS, MINB) k_assemble(const AsmArgs A, const
 #pragma unroll
       for (int s = 0; s < NKV; s++) acc[s] += src[(size_t)s * NEN * PAIRS];
     }
-    if (np == 1) {
-      write_block((int)(x & 0xffu), (int)((x >> 8) & 0xffu), acc);
-    } else {
-      any_split = true;
-      double* ps = s_part + (size_t)(y >> 24) * NKV;
+    const int maxnp = __reduce_max_sync(0xffffffffu, np);
+    for (int k = 1; k < maxnp; k++) {
 #pragma unroll
-      for (int s = 0; s < NKV; s++) ps[s] = acc[s];
-    }
-  }
-  if (__syncthreads_or(any_split)) {   // the first piece of a split block adds the partial sums in piece order
-    for (int t = tid; t < ntask; t += PAIRS) {
-      const int2 tk = t == tid ? my_task : __ldg(A.task + task0 + t);
-      const unsigned x = (unsigned)tk.x, y = (unsigned)tk.y;
-      const int np = (int)((y >> 16) & 0xffu);
-      if (np == 1 || ((y >> 8) & 0xffu) != 0u) continue;
-      const double* ps = s_part + (size_t)(y >> 24) * NKV;
-      double acc[NKV > 0 ? NKV : 1];
-#pragma unroll
-      for (int s = 0; s < NKV; s++) acc[s] = ps[s];
-      for (int k = 1; k < np; k++) {
-#pragma unroll
-        for (int s = 0; s < NKV; s++) acc[s] += ps[(size_t)k * NKV + s];
+      for (int s = 0; s < NKV; s++) {
+        const double v = __shfl_down_sync(0xffffffffu, acc[s], k);
+        if (piece == 0 && k < np) acc[s] += v;
       }
-      write_block((int)(x & 0xffu), (int)((x >> 8) & 0xffu), acc);
     }
+    if (np >= 1 && piece == 0) write_block((int)(x & 0xffu), (int)((x >> 8) & 0xffu), acc);
   }
 }
 

@@ -10,7 +10,6 @@
 
 #define RDC_MAX_NEN 8
 #define RDC_MAX_QP 8
-#define RDC_ASM_MAX_SPLIT 64   /* partial sums of split phase-2 blocks per assembly CTA (shared memory) */
 
 namespace rdc {
 
@@ -72,6 +71,7 @@ struct HostSetup {
   // that the 24-contributor diagonal blocks do not hold up warps whose other lanes have ~6 (task = 2 x int32, see setup.cpp)
   std::vector<int32_t> task;                     // [2 * ntask]
   std::vector<int32_t> task_ptr;                 // [ncta+1]
+  std::vector<int32_t> pair_rec;                 // [ncta * pairs_per_cta * (nen + 4)] padded pair records (setup.cpp)
   int pairs_per_cta = 0;
   // halo exchange (distributed): ghosts are ordered by owner rank, so each neighbour's ghosts are contiguous
   std::vector<int> nbr_rank;                     // neighbours
