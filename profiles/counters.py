@@ -42,6 +42,6 @@ for spec in sys.argv[2:]:
     db[key] = {"kernel": sel[0][col["Kernel Name"]][:90], "launches_averaged": n, "dram_read": mean("dram__bytes_read.sum"),
                "dram_write": mean("dram__bytes_write.sum"), "inst_executed": mean("smsp__inst_executed.sum"),
                "fp64_thread_inst": fp, "registers": mean("launch__registers_per_thread"),
-               "duration_under_ncu_s": mean("gpu__time_duration.sum"), "source": "profiles/" + os.path.basename(rep).replace(".ncu-rep", "_full.csv")}
+               "duration_under_ncu_s": mean("gpu__time_duration.sum"), "source": os.environ.get("COUNTERS_SOURCE", "profiles/" + os.path.basename(rep).replace(".ncu-rep", "_full.csv"))}
 json.dump(db, open(out_path, "w"), indent=1, sort_keys=True)
 print(json.dumps(db, indent=1, sort_keys=True))

@@ -367,6 +367,39 @@ def test_bicgstab_persistent_equals_five_launch(model):
     gpu.close()
 
 
+@pytest.mark.parametrize("ksp,persist", [(2, 0), (2, 1), (0, 0)])
+def test_ripf_every_solve_matches_a_direct_solve_of_its_own_system(ksp, persist):
+    """RIPF mixes HU ~ 1e3 with cell fractions ~ 1e-1 and its convergence test is relative to the norm of the whole
+    vector: two correct solvers agree on the fractions only to ~1e-8 after step 1, and TD = (u - prev)/dt carries that
+    into the next operator (tools/drift_check.py, profiles/r2_ripf_step_error_analysis.log: 2.3e-8 between BiCGStab
+    and the oracle's GMRES from step 2 on).  What CAN be held to a tight bar is every solve against the exact solution
+    of the system it was given: HU within 1e-10, the fractions within the tolerance the criterion implies."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    conn, xyz = cases.mesh(TET4, 12, distort=0.2, length=_length(RIPF))
+    p, u0, ef, nf = cases.case(RIPF, conn, xyz, "full")
+    gpu = cases.gpu_system(RIPF, TET4, conn, xyz, p, u0, ef, nf)
+    gpu.ksp = ksp
+    gpu.set_option("bicg_persist", persist)
+    dt = cases.DT[RIPF]
+    nv = 3
+    for _ in range(3):
+        gpu.time += dt
+        gpu.dt = dt
+        gpu.rotate()
+        gpu.assemble(gpu.time, dt)
+        gpu.linear_solve()
+        x = gpu.get_solution().copy()
+        rows, rowptr, col, val, rhs = gpu.download_csr()
+        xs = spl.spsolve(sp.csr_matrix((val, col, rowptr), shape=(x.size, x.size)).tocsc(), rhs)
+        assert np.linalg.norm(x - xs) <= 1e-10 * np.linalg.norm(xs)
+        assert np.linalg.norm(x[0::nv] - xs[0::nv]) <= 1e-10 * np.linalg.norm(xs[0::nv])
+        for a in (1, 2):   # rtol 1e-12 on a norm ~ 1e3 * sqrt(N) leaves ~1e-9 absolute on fields of size 1e-1
+            assert np.linalg.norm(x[a::nv] - xs[a::nv]) <= 1e-6 * np.linalg.norm(xs[a::nv])
+        gpu.check_solution()
+    gpu.close()
+
+
 @pytest.mark.parametrize("model,n", [(ADPM, 48), (PIHNA, 40)])
 def test_mid_size_step_vs_oracle(model, n):
     """663 552 (ADPM) / 384 000 (PIHNA) tets: large enough that every assembly CTA shape, SpMV tile shape and the
