@@ -18,6 +18,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "p2p_dev.cuh"
 #include "rdc_internal.h"
 
@@ -337,6 +340,24 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                : "memory");
 }
 
+// The same copy with the evict_first L2 priority (createpolicy): the operator is read exactly once per SpMV and is larger
+// than L2 at every size that matters, so its lines should be the first to go -- the Krylov vectors (gathered x, the
+// streams of the vector phases) then survive from one phase to the next.  Measured on one GPU, whole step, same box:
+// 1.35 M tets (the per-rank size of an 8-GPU run) 2.264 -> 2.144 ms, 2.6 M tets 3.898 -> 3.811 ms, 5.3 M and 10.1 M
+// tets unchanged (the vectors alone exceed L2 there).  Marking the leading 32-96 MB of the operator evict_last instead
+// (to keep it resident across the SpMVs, with and without a persisting-L2 set-aside or an access-policy window) gained
+// nothing at any size (tools/pin_sweep.sh, profiles/r2_l2_policy_sweep.log).
+__device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 template <int NKV>
 struct SpmvStage {
   static constexpr int VAL_BYTES = ((SPMV_CAPB * NKV + 2) * 8 + 15) / 16 * 16;
@@ -348,7 +369,7 @@ struct SpmvStage {
 
 template <int NV, unsigned KMASK, int MODE, int STAGES>
 __global__ void __launch_bounds__(RED_THREADS)
-k_spmv_tma(int n_tiles, int uniform16, const int4* __restrict__ tiles, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+k_spmv_tma(int n_tiles, int uniform16, int l2_hint, const int4* __restrict__ tiles, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
            const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y,
            const double* __restrict__ rowscale, const double* __restrict__ w, double* __restrict__ y2, double* partial,
            unsigned* counter, double* out, const int* __restrict__ done, const ArCtx ar) {
@@ -370,6 +391,7 @@ k_spmv_tma(int n_tiles, int uniform16, const int4* __restrict__ tiles, const int
   // down to 16 B) and the 16-byte tile descriptor itself, so that the 255 consumer threads never load a descriptor from
   // global memory (that load, re-issued by every warp in every iteration, drew 17-25 % of the kernel's stall samples);
   // the producer keeps its own descriptors two tiles ahead in registers
+  const unsigned long long pol_stream = l2_policy_evict_first();
   auto issue = [&](int tile, int stage, const int4 t) {
     const int skip_v = (int)(((long long)t.z * NKV) & 1), skip_c = t.z & 3, skip_r = t.x & 3;
     const unsigned vb = (unsigned)(((skip_v + t.w * NKV) * 8 + 15) & ~15);
@@ -378,8 +400,13 @@ k_spmv_tma(int n_tiles, int uniform16, const int4* __restrict__ tiles, const int
     unsigned char* base = s_raw + (size_t)stage * ST::BYTES;
     const unsigned bar = smem_u32(&s_bar[stage]);
     mbar_expect_tx(bar, vb + cb + rb + 16u);
-    bulk_g2s(smem_u32(base), val + ((long long)t.z * NKV - skip_v), vb, bar);
-    bulk_g2s(smem_u32(base + ST::VAL_BYTES), col + (t.z - skip_c), cb, bar);
+    if (l2_hint) {
+      bulk_g2s_hint(smem_u32(base), val + ((long long)t.z * NKV - skip_v), vb, bar, pol_stream);
+      bulk_g2s_hint(smem_u32(base + ST::VAL_BYTES), col + (t.z - skip_c), cb, bar, pol_stream);
+    } else {
+      bulk_g2s(smem_u32(base), val + ((long long)t.z * NKV - skip_v), vb, bar);
+      bulk_g2s(smem_u32(base + ST::VAL_BYTES), col + (t.z - skip_c), cb, bar);
+    }
     bulk_g2s(smem_u32(base + ST::VAL_BYTES + ST::COL_BYTES), rowptr + (t.x - skip_r), rb, bar);
     bulk_g2s(smem_u32(base + ST::DESC_OFF), tiles + tile, 16u, bar);
   };
@@ -537,7 +564,7 @@ int spmv_masks_ok() {
 }
 
 template <int NV, unsigned KMASK, int STAGES>
-static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, int uniform16, const int4* tiles, const int32_t* rowptr, const int32_t* col,
+static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, int uniform16, int l2_hint, const int4* tiles, const int32_t* rowptr, const int32_t* col,
                     const double* val, const double* x, double* y, const double* rowscale, const double* w, double* y2,
                     double* partial, unsigned* counter, double* out, const int* done, const ArCtx& ar) {
   constexpr int SMEM = STAGES * SpmvStage<popc_c(KMASK)>::BYTES;
@@ -553,7 +580,7 @@ static int tma_mode(int mode, unsigned grid, cudaStream_t st, int n_tiles, int u
     if (e != cudaSuccess) return -1;
     attr_done = true;
   }
-#define RDC_TMA_GO(MODE) k_spmv_tma<NV, KMASK, MODE, STAGES><<<grid, RED_THREADS, SMEM, st>>>(n_tiles, uniform16, tiles, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
+#define RDC_TMA_GO(MODE) k_spmv_tma<NV, KMASK, MODE, STAGES><<<grid, RED_THREADS, SMEM, st>>>(n_tiles, uniform16, l2_hint, tiles, rowptr, col, val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
   switch (mode) {
     case SPMV_PLAIN: RDC_TMA_GO(SPMV_PLAIN); break;
     case SPMV_DOT_W: RDC_TMA_GO(SPMV_DOT_W); break;
@@ -597,7 +624,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
     const int per_sm = per_sm_env > 0 ? per_sm_env : (c->nv == 3 ? 6 : 2);  // measured: 2 stages x 6 CTAs/SM beats 3 x 4 by 16 %
     unsigned tg = (unsigned)(W->n_tiles < 148 * per_sm ? W->n_tiles : 148 * per_sm);
     if (tg > (unsigned)SPMV_MAX_GRID) tg = SPMV_MAX_GRID;   // W->partial holds 2 * SPMV_MAX_GRID per-CTA partials
-#define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles_uniform, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
+#define RDC_TMA_MODEL(NVV, KM, STG) tma_mode<NVV, KM, STG>(mode, tg, c->stream, W->n_tiles, W->tiles_uniform, c->opt.l2_evict_first, W->tiles, c->d_rowptr, c->d_col, c->d_val, x, y, rowscale, w, y2, partial, counter, out, done, ar)
     int trc;
     switch (c->model) {
       case RDC_ADPM: trc = stages_env == 3 ? RDC_TMA_MODEL(3, KM_ADPM, 3) : RDC_TMA_MODEL(3, KM_ADPM, 2); break;
@@ -1502,7 +1529,7 @@ struct PersistHalo {
   int on = 0, nv = 1;
 };
 struct PersistArgs {
-  int n_tiles; int uniform16; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val;
+  int n_tiles; int uniform16; int l2_hint; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val;
   const double* scale; const double* b;
   size_t n;
   double *x, *r, *r0, *v, *s, *t, *p0, *p1;
@@ -1707,7 +1734,7 @@ __device__ __noinline__ void grid_allreduce(double v0, double v1, int nval, doub
 // budget of the kernel (40 registers at 6 CTAs/SM) for its own loop; inlined, the loop-carried state of the solver was
 // spilled INSIDE the tile loop (800 bytes of spill traffic per thread, +12 % per iteration).
 struct SpmvOp {
-  int n_tiles; int uniform16; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val; const double* scale;
+  int n_tiles; int uniform16; int l2_hint; const int4* tiles; const int32_t* rowptr; const int32_t* col; const double* val; const double* scale;
 };
 struct SpmvRes { double d0, d1; unsigned gi; };
 template <int NV, unsigned KMASK, int MODE>
@@ -1722,6 +1749,7 @@ __device__ __noinline__ SpmvRes persist_spmv(const SpmvOp A, const double* __res
   const int4* __restrict__ tiles = A.tiles;
   const int n_tiles = A.n_tiles;
   double d[2] = {0.0, 0.0};
+  const unsigned long long pol_stream = l2_policy_evict_first();
   auto issue = [&](int tile, unsigned slot, const int4 t) {
     const int skip_v = (int)(((long long)t.z * NKV) & 1), skip_c = t.z & 3, skip_r = t.x & 3;
     const unsigned vb = (unsigned)(((skip_v + t.w * NKV) * 8 + 15) & ~15);
@@ -1730,8 +1758,13 @@ __device__ __noinline__ SpmvRes persist_spmv(const SpmvOp A, const double* __res
     unsigned char* base = s_raw + (size_t)(slot % STAGES) * ST::BYTES;
     const unsigned bar = smem_u32(&s_bar[slot % STAGES]);
     mbar_expect_tx(bar, vb + cb + rb + 16u);
-    bulk_g2s(smem_u32(base), A.val + ((long long)t.z * NKV - skip_v), vb, bar);
-    bulk_g2s(smem_u32(base + ST::VAL_BYTES), A.col + (t.z - skip_c), cb, bar);
+    if (A.l2_hint) {
+      bulk_g2s_hint(smem_u32(base), A.val + ((long long)t.z * NKV - skip_v), vb, bar, pol_stream);
+      bulk_g2s_hint(smem_u32(base + ST::VAL_BYTES), A.col + (t.z - skip_c), cb, bar, pol_stream);
+    } else {
+      bulk_g2s(smem_u32(base), A.val + ((long long)t.z * NKV - skip_v), vb, bar);
+      bulk_g2s(smem_u32(base + ST::VAL_BYTES), A.col + (t.z - skip_c), cb, bar);
+    }
     bulk_g2s(smem_u32(base + ST::VAL_BYTES + ST::COL_BYTES), A.rowptr + (t.x - skip_r), rb, bar);
     bulk_g2s(smem_u32(base + ST::DESC_OFF), tiles + tile, 16u, bar);   // the consumers read the descriptor from the stage
   };
@@ -1929,7 +1962,7 @@ __global__ void __launch_bounds__(RED_THREADS, (NV == 3 ? 6 : 2)) k_bicgstab_per
   // r = r0 = B (b - A x), <r,r>, ||B b||^2 (the ghosts of x were exchanged by the host-side launch before)
   unsigned long long t_resid = 0;
   SpmvOp op;
-  op.n_tiles = A.n_tiles; op.uniform16 = A.uniform16; op.tiles = A.tiles; op.rowptr = A.rowptr; op.col = A.col; op.val = A.val; op.scale = A.scale;
+  op.n_tiles = A.n_tiles; op.uniform16 = A.uniform16; op.l2_hint = A.l2_hint; op.tiles = A.tiles; op.rowptr = A.rowptr; op.col = A.col; op.val = A.val; op.scale = A.scale;
   {
     const SpmvRes sr = persist_spmv<NV, KMASK, SPMV_RESID>(op, A.x, A.r, A.b, A.r0, s_raw, s_bar, gi);
     gi = sr.gi;
@@ -2084,7 +2117,7 @@ static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, 
   if ((rc = ensure_gmres(c, 1))) return rc;   // borrow V for one more vector
   if ((rc = refresh_u_ghosts(c))) return rc;
   PersistArgs A;
-  A.n_tiles = W->n_tiles; A.uniform16 = W->tiles_uniform; A.tiles = W->tiles; A.rowptr = c->d_rowptr; A.col = c->d_col; A.val = c->d_val;
+  A.n_tiles = W->n_tiles; A.uniform16 = W->tiles_uniform; A.l2_hint = c->opt.l2_evict_first; A.tiles = W->tiles; A.rowptr = c->d_rowptr; A.col = c->d_col; A.val = c->d_val;
   A.scale = scale; A.b = c->d_rhs;
   A.n = (size_t)c->S.n_owned * c->nv;
   A.x = c->d_u; A.r = W->t1; A.r0 = W->t2; A.v = W->t4; A.s = W->hs; A.t = W->V; A.p0 = W->t3; A.p1 = W->hp2;
