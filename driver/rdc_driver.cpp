@@ -123,13 +123,35 @@ static Mesh read_gmsh(const std::string& path) {
   return m;
 }
 
+// rows x cols numbers; blank lines and lines starting with '#' are skipped (proteas.C:296-301)
 static std::vector<double> read_table(const std::string& path, size_t rows, int cols) {
   std::ifstream f(path);
   if (!f) die("cannot open " + path);
-  std::vector<double> v(rows * cols);
-  for (auto& x : v)
-    if (!(f >> x)) die("short field file " + path);
+  std::vector<double> v;
+  v.reserve(rows * cols);
+  std::string line;
+  while (v.size() < rows * cols && std::getline(f, line)) {
+    const size_t a = line.find_first_not_of(" \t\r");
+    if (a == std::string::npos || line[a] == '#') continue;
+    std::istringstream iss(line);
+    double x;
+    while (iss >> x) v.push_back(x);
+  }
+  if (v.size() < rows * cols) die("short field file " + path);
+  v.resize(rows * cols);
   return v;
+}
+
+// utils.h:268-288 export_integers: the integers of a blank-separated list
+static std::set<int> integers_of(const std::string& s) {
+  std::set<int> out;
+  std::istringstream iss(s);
+  std::string w;
+  while (iss >> w) {
+    int n;
+    if (std::istringstream(w) >> n) out.insert(n);
+  }
+  return out;
 }
 
 template <size_t NK>
@@ -146,15 +168,21 @@ static std::vector<double> flat_params(const ParamKey (&table)[NK], const Input&
 int main(int argc, char** argv) {
   std::string model_name = "adpm", in_path, sol_out;
   int ksp = RDC_KSP_BICGSTAB;
+  bool vtu_binary = false, rdc_only = false;
   for (int a = 1; a < argc; a++) {
     if (!strcmp(argv[a], "-m") && a + 1 < argc) model_name = argv[++a];
     else if (!strncmp(argv[a], "ksp=", 4)) ksp = atoi(argv[a] + 4);
     else if (!strncmp(argv[a], "solution_out=", 13)) sol_out = argv[a] + 13;
+    else if (!strcmp(argv[a], "vtu=binary")) vtu_binary = true;
+    else if (!strcmp(argv[a], "vtu=ascii")) vtu_binary = false;
+    else if (!strcmp(argv[a], "solid=off")) rdc_only = true;
     else in_path = argv[a];
   }
-  if (in_path.empty()) die("usage: rdc_driver -m adpm|pihna|ripf <input.dat> [ksp=2] [solution_out=file]");
-  const int model = model_name == "adpm" ? RDC_ADPM : model_name == "pihna" ? RDC_PIHNA : model_name == "ripf" ? RDC_RIPF : -1;
-  if (model < 0) die("unknown model " + model_name + " (main.C:24-38 knows adpm, pihna, proteas, ripf)");
+  if (in_path.empty())
+    die("usage: rdc_driver -m adpm|pihna|ripf|proteas|coupled_hcc <input.dat> [ksp=2] [vtu=binary] [solid=off] [solution_out=file]");
+  const int model = model_name == "adpm" ? RDC_ADPM : model_name == "pihna" ? RDC_PIHNA : model_name == "ripf" ? RDC_RIPF
+                  : model_name == "proteas" ? RDC_PROTEAS : (model_name == "coupled_hcc" || model_name == "hcc") ? RDC_HCC : -1;
+  if (model < 0) die("unknown model " + model_name + " (main.C:24-38 knows adpm, pihna, proteas, ripf; coupled_hcc.C is the fifth)");
   const int nv = rdc_model_nvars(model);
   const size_t slash = in_path.find_last_of('/');
   const std::string dir = slash == std::string::npos ? std::string() : in_path.substr(0, slash + 1);
@@ -164,14 +192,27 @@ int main(int argc, char** argv) {
   std::vector<double> p;
   if (model == RDC_ADPM) p = flat_params(kAdpmTable, in);
   else if (model == RDC_PIHNA) p = flat_params(kPihnaTable, in);
+  else if (model == RDC_PROTEAS) p = flat_params(kProteasTable, in);
+  else if (model == RDC_HCC) p = flat_params(kHccTable, in);
   else {
     p = flat_params(kRipfTable, in);
     if (!in.kv.count("volume_fraction/max_vacant")) p[RIPF_VF_MAX_VACANT] = 1.0 - p[RIPF_VF_MIN_VACANT];   // ripf.C:181-182
   }
   if ((int)p.size() != rdc_model_nparams(model)) die("parameter table out of date: run driver/gen_tables.py");
-  const double dt = in.real("time_step", 1.0e-9);
-  const int n_steps = in.integer("time_step_number", 1);
+  // coupled_hcc.C:184-187 names its step count differently and defaults the step to 1
+  const double dt = in.real("time_step", model == RDC_HCC ? 1.0 : 1.0e-9);
+  const int n_steps = in.integer(model == RDC_HCC ? "number_of_time_steps" : "time_step_number", 1);
   const int out_step = in.integer("output_step", 0);
+  // output steps: every output_step-th, else the integers of "output_time_points" (default: the last step), adpm.C /
+  // proteas.C:144-163 / coupled_hcc.C
+  std::set<int> out_points;
+  if (out_step > 0) for (int t = out_step; t <= n_steps; t += out_step) out_points.insert(t);
+  else out_points = integers_of(in.str("output_time_points", std::to_string(n_steps)));
+  if (model == RDC_PROTEAS && in.integer("refinement_step", n_steps + 1) <= n_steps)
+    die("refinement_step <= time_step_number asks for adaptive mesh refinement (proteas.C:82-83), which this driver does not do");
+  if (model == RDC_HCC && !rdc_only)
+    die("coupled_hcc.C:117-132 solves the solid-mechanics equilibrium at the loading time points and moves the mesh; that path is "
+        "not part of this driver.  Pass solid=off to run the reaction-diffusion system on the fixed mesh (no loading steps).");
 
   // ---- mesh and initial fields ---------------------------------------------------------------------------------
   Mesh mesh = read_gmsh(dir + in.str("input_GMSH", "input.msh"));
@@ -198,6 +239,11 @@ int main(int argc, char** argv) {
   if (model == RDC_RIPF) {
     std::vector<double> rt = read_table(dir + in.str("input_nodal_RT", "input.nodal~RT"), (size_t)N, 2);
     ck(rdc_set_nodal_field(ctx, 0, rt.data(), 2), "rdc_set_nodal_field");
+  }
+  std::vector<double> aux;   // PROTEAS: the AUX system (HU, RTD), proteas.C:37-41,218-268; also written to ParaView
+  if (model == RDC_PROTEAS) {
+    aux = read_table(dir + in.str("input_nodal_aux", "input_aux.nd"), (size_t)N, 2);
+    ck(rdc_set_nodal_field(ctx, 0, aux.data(), 2), "rdc_set_nodal_field");
   }
   ck(rdc_set_solution(ctx, u0.data()), "rdc_set_solution");
   ck(rdc_set_subdomains(ctx, n_regions > 1 ? region.data() : nullptr, n_regions), "rdc_set_subdomains");
@@ -249,6 +295,8 @@ int main(int argc, char** argv) {
       tot.w[1] = tot.w[2] = tot.w[3] = 1.0;   // (n + c + h + v) / Kappa_k
       csv << time << ',' << (long long)nv * N << ',' << volume(1, &act)[0] << ',' << volume(1, &nec)[0] << ',' << volume(1, &vas)[0]
           << ',' << volume(1, &tot)[0] << std::endl;
+    } else if (model == RDC_PROTEAS || model == RDC_HCC) {
+      // proteas.C:53-55 opens the CSV and never writes to it; coupled_hcc.C has none
     } else {   // ripf.C:777-864 (no header: it is commented out in the reference)
       const double HUmin = p[RIPF_HU_MIN], HUmax = p[RIPF_HU_MAX];
       rdc_range_cond cc[2] = {cond1(0, 1.0, in.real("range_cc/HU/min", HUmin), in.real("range_cc/HU/max", HUmax)),
@@ -259,20 +307,34 @@ int main(int argc, char** argv) {
     }
   };
   // ParaView output (paraview.update_pvd, adpm.C:55,82): only when input.dat names output_PARAVIEW
-  static const char* kVarNames[3][5] = {{"PrP", "A_b", "Tau", "", ""}, {"n", "c", "h", "v", "a"}, {"HU", "cc", "fb", "", ""}};
+  static const char* kVarNames[5][5] = {{"PrP", "A_b", "Tau", "", ""}, {"n", "c", "h", "v", "a"}, {"HU", "cc", "fb", "", ""},
+                                        {"hos", "tum", "nec", "vsc", "oed"}, {"l", "c", "n", "", ""}};   // proteas.C:28-32, coupled_hcc.C:33-35
   std::vector<std::string> var_names;
-  for (int a = 0; a < nv; a++) var_names.push_back(kVarNames[model == RDC_ADPM ? 0 : model == RDC_PIHNA ? 1 : 2][a]);
+  const int name_row = model == RDC_ADPM ? 0 : model == RDC_PIHNA ? 1 : model == RDC_RIPF ? 2 : model == RDC_PROTEAS ? 3 : 4;
+  for (int a = 0; a < nv; a++) var_names.push_back(kVarNames[name_row][a]);
+  const int n_extra = model == RDC_PROTEAS ? 2 : 0;   // Paraview_IO writes every system: PROTEAS_model, then AUX
+  if (n_extra) { var_names.push_back("HU"); var_names.push_back("RTD"); }
   const VtuMesh vmesh = {mesh.nen, &mesh.xyz, &mesh.conn, &mesh.subdomain, nullptr};
   std::unique_ptr<PvdCollection> pvd;
-  if (in.kv.count("output_PARAVIEW")) {
-    pvd.reset(new PvdCollection(dir + in.str("output_PARAVIEW", "output4paraview")));
+  const char* pv_key = model == RDC_PROTEAS ? "output_Paraview" : "output_PARAVIEW";   // proteas.C:126 spells it differently
+  if (in.kv.count(pv_key)) {
+    pvd.reset(new PvdCollection(dir + in.str(pv_key, "output4paraview"), vtu_binary));
     if (!pvd->ok()) die("cannot open the .pvd collection");
   }
-  std::vector<double> u_host((size_t)N * nv);
+  std::vector<double> u_host((size_t)N * nv), u_out;
   auto update_pvd = [&](unsigned t) {
     if (!pvd) return;
     ck(rdc_get_solution(ctx, u_host.data()), "rdc_get_solution");   // the only device->host copy of the solution
-    if (!pvd->add(vmesh, var_names, u_host, t)) die("cannot write the .vtu file");
+    const std::vector<double>* vals = &u_host;
+    if (n_extra) {   // append the AUX columns
+      u_out.resize((size_t)N * (nv + n_extra));
+      for (int64_t n = 0; n < N; n++) {
+        for (int a = 0; a < nv; a++) u_out[(size_t)n * (nv + n_extra) + a] = u_host[(size_t)n * nv + a];
+        for (int a = 0; a < n_extra; a++) u_out[(size_t)n * (nv + n_extra) + nv + a] = aux[(size_t)n * n_extra + a];
+      }
+      vals = &u_out;
+    }
+    if (!pvd->add(vmesh, var_names, *vals, t)) die("cannot write the .vtu file");
   };
   save_solution(0.0);   // adpm.C:54
   update_pvd(0);        // adpm.C:55
@@ -287,8 +349,7 @@ int main(int argc, char** argv) {
     ck(rdc_step(ctx, time, dt, ksp, RDC_PC_JACOBI, 1e-12, 5000, 30, &its, &res), "rdc_step");
     its_total += its;
     printf(" ==== Step %4d out of %4d (Time=%9g) ==== its %d res %.3e\n", t, n_steps, time, its, res);
-    const bool out = out_step ? (t % out_step == 0) : (t == in.integer("output_time_points", n_steps));
-    if (out) { save_solution(time); update_pvd((unsigned)t); }
+    if (out_points.count(t)) { save_solution(time); update_pvd((unsigned)t); }
   }
   if (!sol_out.empty()) {
     std::vector<double> u((size_t)N * nv);

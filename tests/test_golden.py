@@ -129,7 +129,8 @@ int main(int argc, char** argv) {
   VtuMesh m = {4, &xyz, &conn, &sub, nullptr};
   std::vector<double> u = {1,10, 2,20, 3,30, 4,1e-320, 5,50};
   PvdCollection pvd(argv[1]);
-  return pvd.add(m, {"A", "B"}, u, 0) && pvd.add(m, {"A", "B"}, u, 20) ? 0 : 1;
+  PvdCollection bin(std::string(argv[1]) + "_bin", true);
+  return pvd.add(m, {"A", "B"}, u, 0) && pvd.add(m, {"A", "B"}, u, 20) && bin.add(m, {"A", "B"}, u, 20) ? 0 : 1;
 }
 ''')
     exe = tmp_path / "t"
@@ -148,3 +149,20 @@ int main(int argc, char** argv) {
     assert np.array_equal(arr["region_ID"], [7, 3]) and np.array_equal(arr["processor_ID"], [0, 0])
     assert np.array_equal(arr["connectivity"], [0, 1, 2, 3, 1, 2, 3, 4])
     assert np.array_equal(arr["offsets"], [4, 8]) and np.array_equal(arr["types"], [10, 10])
+    # the raw appended form: same arrays, same order, UInt64 byte counts in front of every block
+    raw = open(base + "_bin-20.vtu", "rb").read()
+    cut = raw.index(b'<AppendedData encoding="raw">')
+    start = raw.index(b"_", cut) + 1
+    root = ET.fromstring(raw[:cut] + b"</VTKFile>")
+    assert root.get("header_type") == "UInt64" and root.get("byte_order") == "LittleEndian"
+    names = []
+    for a in root.iter("DataArray"):
+        assert a.get("format") == "appended"
+        off = start + int(a.get("offset"))
+        nbytes = int(np.frombuffer(raw[off:off + 8], dtype="<u8")[0])
+        dt = "<f8" if a.get("type") == "Float64" else "<i4"
+        got = np.frombuffer(raw[off + 8:off + 8 + nbytes], dtype=dt)
+        assert np.array_equal(got, arr[a.get("Name")]), a.get("Name")
+        names.append(a.get("Name"))
+    assert names == [a.get("Name") for a in piece.iter("DataArray")]
+    assert raw[start + int(list(root.iter("DataArray"))[-1].get("offset")) + 8 + 8:].strip().startswith(b"</AppendedData>")

@@ -105,6 +105,86 @@ def test_cpp_driver_pihna_ripf(tmp_path, model):
     gpu.close()
 
 
+def _read_appended_vtu(path):
+    """{name: array} of a raw-appended .vtu written by driver/vtu_writer.h"""
+    import xml.etree.ElementTree as ET
+    raw = open(path, "rb").read()
+    cut = raw.index(b'<AppendedData encoding="raw">')
+    start = raw.index(b"_", cut) + 1
+    root = ET.fromstring(raw[:cut] + b"</VTKFile>")
+    out = {}
+    for a in root.iter("DataArray"):
+        off = start + int(a.get("offset"))
+        nbytes = int(np.frombuffer(raw[off:off + 8], dtype="<u8")[0])
+        out[a.get("Name")] = np.frombuffer(raw[off + 8:off + 8 + nbytes], dtype="<f8" if a.get("type") == "Float64" else "<i4")
+    return out
+
+
+@pytest.mark.parametrize("model", [cases.PROTEAS, cases.HCC])
+def test_cpp_driver_proteas_hcc(tmp_path, model):
+    """The last two models through the stand-alone driver (proteas.C:16-90, coupled_hcc.C:16-142 with the solid solver
+    switched off): '#'-commented nodal files, the AUX system's file, output_time_points as a list, the model's own
+    key names (time_step_number / number_of_time_steps, output_Paraview / output_PARAVIEW), raw-appended VTU output."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
+    conn, xyz = cases.mesh(cases.TET4, 6, distort=0.2)
+    p, u0, ef, nf = cases.case(model, conn, xyz, "full")
+    nv = cases.P.NVARS[model]
+    d = str(tmp_path)
+    _write_gmsh(os.path.join(d, "cube.msh"), conn, xyz, np.ones(conn.shape[0], dtype=int))
+    U0 = np.asarray(u0).reshape(-1, nv)
+    with open(os.path.join(d, "nodal.dat"), "w") as f:
+        f.write("# initial state\n\n")
+        for k, row in enumerate(U0):
+            if k == 3 and model == cases.PROTEAS:
+                f.write("# a comment between the rows\n")
+            f.write(" ".join("%.17g" % v for v in row) + "\n")
+    nsteps, dt = 5, cases.DT[model]
+    extra = "input_GMSH = cube.msh\ninput_nodal = nodal.dat\n"
+    if model == cases.PROTEAS:
+        np.savetxt(os.path.join(d, "aux.dat"), np.asarray(nf).reshape(-1, 2), fmt="%.17g", header="HU RTD")
+        extra += f"input_nodal_aux = aux.dat\noutput_Paraview = view\ntime_step_number = {nsteps}\ntime_step = {dt}\n"
+    else:
+        extra += f"output_PARAVIEW = view\nnumber_of_time_steps = {nsteps}\ntime_step = {dt}\n"
+    extra += "output_time_points = '2 5'\n"
+    _write_input(os.path.join(d, "input.dat"), model, p, extra)
+    sol = os.path.join(d, "u.bin")
+    name = "proteas" if model == cases.PROTEAS else "coupled_hcc"
+    args = [os.path.join(ROOT, "driver", "rdc_driver"), "-m", name, os.path.join(d, "input.dat"), "ksp=2", "vtu=binary",
+            "solution_out=" + sol]
+    if model == cases.HCC:
+        refused = subprocess.run(args, capture_output=True, text=True, timeout=300)
+        assert refused.returncode != 0 and "solid=off" in refused.stderr      # the solid-mechanics coupling is not there: said loudly
+        args.append("solid=off")
+    out = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    u_drv = np.fromfile(sol)
+
+    gpu = cases.gpu_system(model, cases.TET4, conn, xyz, p, u0, ef, nf)
+    gpu.ksp = 2
+    orc = cases.oracle_problem(model, cases.TET4, conn, xyz, p, u0, ef, nf)
+    snap = {}
+    for t in range(1, nsteps + 1):
+        gpu.step(dt)
+        orc.step(dt, pc=O.PC_ILU)
+        if t in (2, 5):
+            snap[t] = gpu.get_solution().reshape(-1, nv).copy()
+    assert np.array_equal(u_drv, gpu.get_solution())
+    assert np.linalg.norm(u_drv - orc.u) <= 1e-8 * np.linalg.norm(orc.u)
+    gpu.close()
+    # ParaView output: steps 0, 2 and 5; every variable of the model (and PROTEAS' AUX system) as its own array
+    assert sorted(f for f in os.listdir(d) if f.endswith(".vtu")) == ["view-0.vtu", "view-2.vtu", "view-5.vtu"]
+    names = ["hos", "tum", "nec", "vsc", "oed"] if model == cases.PROTEAS else ["l", "c", "n"]
+    for t in (2, 5):
+        arr = _read_appended_vtu(os.path.join(d, f"view-{t}.vtu"))
+        for a, nm in enumerate(names):
+            want = snap[t][:, a].copy()
+            want[np.abs(want) <= 1e-300] = 0.0
+            assert np.array_equal(arr[nm], want), nm
+        assert np.array_equal(arr["position"].reshape(-1, 3), xyz) and np.array_equal(arr["connectivity"].reshape(-1, 4), conn)
+        if model == cases.PROTEAS:
+            assert np.array_equal(arr["HU"], np.asarray(nf).reshape(-1, 2)[:, 0]) and np.array_equal(arr["RTD"], np.asarray(nf).reshape(-1, 2)[:, 1])
+
+
 def test_cpp_driver_matches_python_mirror_and_oracle(tmp_path):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
     conn, xyz = cases.mesh(cases.TET4, 6, distort=0.2)
