@@ -23,7 +23,9 @@ Krylov solve (BiCGStab + Jacobi by default, --ksp 0 = libMesh's GMRES(30)) to rt
   * ksp_gmres30 : (N = 1) the same steps with libMesh's default Krylov method, GMRES(30), for reference
 N > 1 (torchrun): strong scaling of the same mesh, METIS node partition, ghost exchange + all-reduce over NVLink
 peer memory inside the Krylov kernels (NCCL for set-up and as fallback).  --model pihna: secondary 5-species case.
---impl reference: times the CPU port only (the real rdcFEs binary needs libMesh/PETSc/MPI: not installable).
+--impl reference: times the CPU port on all host cores (the real rdcFEs binary needs libMesh/PETSc/MPI: not installable);
+its line also carries `reference_assembly_sample`: the reference's OWN assemble_adpm (oracle/_ref, src/adpm.C compiled
+unchanged, serial) timed next to the port on one thread on a bounded sample, with the two operators compared.
 """
 import argparse
 import json
@@ -141,6 +143,39 @@ def cpu_port_run(n, steps, warmup, nthreads, keep_state=None):
     return float(np.mean(times)), conn.shape[0], float(np.mean(its_all)), float(np.mean(ta)), float(np.mean(ts))
 
 
+def reference_assembly_sample(n_s=24):
+    """The reference's OWN assemble_adpm (oracle/_ref: src/adpm.C compiled unchanged against the serial libMesh stand-in)
+    timed on a bounded sample next to the port on ONE thread, with the two operators compared: shows what the port's
+    per-element cost is relative to the reference's own code.  None when oracle/_ref is not built."""
+    try:
+        from oracle import oracle as O
+        from oracle import ref as R
+        if not R.available():
+            return None
+        from rdcfes_b200 import params as P
+        conn, xyz, params, u0, tracts = workload(n_s)
+        rp = R.RefProblem(P.ADPM, 4, conn, xyz, params, u0, elem_field=tracts)
+        t0 = time.perf_counter()
+        val_r, rhs_r = rp.assemble(DT, DT)
+        t_ref = time.perf_counter() - t0
+        pr = O.Problem(O.ADPM, O.TET4, conn, xyz, params, u0, elem_field=tracts, nthreads=1)
+        pr.u_old = pr.u.copy()
+        t0 = time.perf_counter()
+        val_p, rhs_p = pr.assemble(DT, DT)
+        t_port = time.perf_counter() - t0
+        E = conn.shape[0]
+        same = bool(val_r.shape == val_p.shape)
+        diff = float(np.abs(val_r - val_p).max() / np.abs(val_r).max()) if same else None
+        rp.close()
+        return {"kind": "reference", "what": "assemble_adpm of the reference (src/adpm.C unchanged, serial libMesh stand-in with a "
+                                             "std::map-per-row matrix) against the port on one thread, same mesh and fields",
+                "sample": f"n={n_s} ({E} tets)", "cores": 1, "reference_s": t_ref, "port_s": t_port,
+                "reference_us_per_tet": 1e6 * t_ref / E, "port_us_per_tet": 1e6 * t_port / E,
+                "max_abs_diff_over_max": diff}
+    except Exception as exc:   # a checker must never break the reference arm
+        return {"kind": "reference", "error": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (our libMesh-free port, oracle/) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -161,6 +196,9 @@ def run_reference(args):
                             "sample": f"n={n_sample} ({E} tets) timed {sec:.3f} s/step ({ta:.3f} assemble + {ts:.3f} solve, "
                                       f"{its:.0f} GMRES(30)+BJacobi/ILU0 its), scaled x{E_full / E:.1f} by element count"},
            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    ras = reference_assembly_sample()
+    if ras is not None:
+        out["reference_assembly_sample"] = ras
     print(json.dumps(out))
 
 
