@@ -24,7 +24,7 @@ static const OptName kOptions[] = {
     {"spmv_ctas_per_sm", &rdc_options::spmv_ctas_per_sm}, {"tma_ctas_per_sm", &rdc_options::tma_ctas_per_sm},
     {"tma_stages", &rdc_options::tma_stages}, {"sync_every", &rdc_options::sync_every},
     {"p2p_fused_ar", &rdc_options::p2p_fused_ar}, {"p2p_fused_halo", &rdc_options::p2p_fused_halo},
-    {"node_order", &rdc_options::node_order}, {"bicg_persist", &rdc_options::bicg_persist}, {"persist_timing", &rdc_options::persist_timing}, {"l2_evict_first", &rdc_options::l2_evict_first}, {"trace", &rdc_options::trace}};
+    {"node_order", &rdc_options::node_order}, {"bicg_persist", &rdc_options::bicg_persist}, {"persist_timing", &rdc_options::persist_timing}, {"l2_evict_first", &rdc_options::l2_evict_first}, {"vec_reverse", &rdc_options::vec_reverse}, {"trace", &rdc_options::trace}};
 
 static void options_from_env(rdc_options& o) {
   for (const OptName& k : kOptions) {

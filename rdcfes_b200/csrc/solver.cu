@@ -1334,7 +1334,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_p(size_t n, int it, int rn, 
 // s = r - alpha v   (+ ghost exchange of s, see HaloBundle)
 __global__ void __launch_bounds__(RED_THREADS) k_bi_s(size_t n, int ro, const double* __restrict__ r, const double* __restrict__ v,
                                                       double* __restrict__ s, const double* __restrict__ D,
-                                                      const int* __restrict__ state, const HaloBundle hb) {
+                                                      const int* __restrict__ state, const HaloBundle hb, const int rev) {
   if (state[0]) return;
   const double alpha = D[ro] / D[D_R0V];
   if ((int)blockIdx.x < hb.total) {
@@ -1345,19 +1345,27 @@ __global__ void __launch_bounds__(RED_THREADS) k_bi_s(size_t n, int ro, const do
     return;
   }
   const size_t first = (blockIdx.x - hb.total) * (size_t)blockDim.x + threadIdx.x, step = (size_t)(gridDim.x - hb.total) * blockDim.x;
-  for (size_t i = first; i < n; i += step) s[i] = fma(-alpha, v[i], r[i]);
+  // back to front: the SpMV before this kernel wrote v in ascending row order, so its tail is what is still in L2; and the
+  // head of s, written last here, is what the next SpMV's first tiles gather
+  for (size_t k = first; k < n; k += step) {
+    const size_t i = rev ? n - 1 - k : k;
+    s[i] = fma(-alpha, v[i], r[i]);
+  }
 }
 // x += alpha p + omega s ; r = s - omega t ; out = {<r0,r>, <r,r>}
 __global__ void __launch_bounds__(RED_THREADS) k_bi_xr(size_t n, int ro, double* __restrict__ x, const double* __restrict__ p,
                                                        const double* __restrict__ s, const double* __restrict__ t,
                                                        double* __restrict__ r, const double* __restrict__ r0,
                                                        const double* __restrict__ D, double* partial, unsigned* counter,
-                                                       double* out, const int* __restrict__ state, const ArCtx ar) {
+                                                       double* out, const int* __restrict__ state, const ArCtx ar, const int rev) {
   if (state[0]) return;
   const double alpha = D[ro] / D[D_R0V];
   const double omega = D[D_TT] != 0.0 ? D[D_TS] / D[D_TT] : 0.0;
   double acc[2] = {0.0, 0.0};
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  // back to front for the same reason as k_bi_s (t was written in ascending row order by the SpMV just before); the
+  // p-update that follows runs front to back and meets the head of r, written last here, in L2
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = rev ? n - 1 - k : k;
     const double si = s[i];
     x[i] = fma(omega, si, fma(alpha, p[i], x[i]));
     const double ri = fma(-omega, t[i], si);
@@ -1476,7 +1484,7 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
     TR.mark("ar1", c->stream);
     hb = HaloBundle();
     if (fuse_halo && (rc = halo_bundle(c, s, &hb))) return rc;
-    k_bi_s<<<vg + hb.total, RED_THREADS, 0, c->stream>>>(n, rn, r, v, s, D, W->state, hb);
+    k_bi_s<<<vg + hb.total, RED_THREADS, 0, c->stream>>>(n, rn, r, v, s, D, W->state, hb, c->opt.vec_reverse);
     TR.mark("s_update", c->stream);
     if (!fuse_halo && (rc = halo_exchange(c, s, true))) return rc;
     TR.mark("halo_s", c->stream);
@@ -1487,7 +1495,7 @@ static int bicgstab(rdc_ctx* c, const double* scale, double rtol, int maxits, in
     TR.mark("ar2", c->stream);
     double* xr_out = D + D_XR0 + 2 * (it & 1);
     ar = ar_begin(c, &fused);
-    k_bi_xr<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, rn, c->d_u, p, s, t, r, r0, D, W->partial, W->counter, xr_out, W->state, ar);
+    k_bi_xr<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(n, rn, c->d_u, p, s, t, r, r0, D, W->partial, W->counter, xr_out, W->state, ar, c->opt.vec_reverse);
     TR.mark("xr_update", c->stream);
     if (!fused && (rc = allreduce_sum(c, xr_out, 2, true))) return rc;
     TR.mark("ar3", c->stream);
