@@ -27,7 +27,8 @@ _p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "rdc_oracle.c")
-    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
+    src2 = os.path.join(_HERE, "solid_oracle.c")
+    if force or not os.path.exists(so) or any(os.path.exists(s) and os.path.getmtime(so) < os.path.getmtime(s) for s in (src, src2)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 

@@ -1286,3 +1286,6 @@ int orc_step(int model, int elem_type, int64_t N, int64_t E, const int32_t* conn
   }
   return rc;
 }
+
+/* the solid-mechanics Newton path uses the FE tables, pattern builder and GMRES above */
+#include "solid_oracle.c"

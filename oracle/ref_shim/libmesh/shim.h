@@ -29,6 +29,7 @@
 #include <stdexcept>
 #include <string>
 #include <typeinfo>
+#include <tuple>
 #include <vector>
 
 #define LIBMESH_DIM 3
@@ -60,6 +61,9 @@ static const Real TOLERANCE = 1.e-6;
 static std::ostream& out = std::cout;
 static std::ostream& err = std::cerr;
 template <class... A> inline void libmesh_ignore(const A&...) {}
+template <class T, class U> inline T cast_ref(U& u) { return dynamic_cast<T>(u); }
+template <class T, class U> inline T cast_int(U u) { return static_cast<T>(u); }
+inline bool libmesh_isnan(double x) { return std::isnan(x); }
 inline processor_id_type global_processor_id() { return 0; }
 inline processor_id_type global_n_processors() { return 1; }
 
@@ -127,6 +131,7 @@ class TypeTensor {
   TypeTensor operator*(const T f) const { TypeTensor r; for (int i = 0; i < 9; i++) r.c[i] = c[i] * f; return r; }
   TypeTensor operator/(const T f) const { TypeTensor r; for (int i = 0; i < 9; i++) r.c[i] = c[i] / f; return r; }
   TypeTensor& operator*=(const T f) { for (T& v : c) v *= f; return *this; }
+  TypeTensor& operator/=(const T f) { for (T& v : c) v /= f; return *this; }
   TypeTensor operator*(const TypeTensor& p) const {
     TypeTensor r;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) r(i, j) += (*this)(i, k) * p(k, j);
@@ -185,6 +190,7 @@ class DenseVector {
   DenseVector& operator=(std::initializer_list<T> l) { v.assign(l.begin(), l.end()); return *this; }
   DenseVector& operator+=(const DenseVector& o) { for (size_t i = 0; i < v.size(); i++) v[i] += o.v[i]; return *this; }
   DenseVector& operator*=(T f) { for (T& x : v) x *= f; return *this; }
+  void scale(T f) { for (T& x : v) x *= f; }
   void add(T f, const DenseVector& o) { for (size_t i = 0; i < v.size(); i++) v[i] += f * o.v[i]; }
 };
 template <class T>
@@ -202,6 +208,7 @@ class DenseMatrix {
   void zero() { std::fill(a.begin(), a.end(), T(0)); }
   DenseMatrix& operator+=(const DenseMatrix& o) { for (size_t i = 0; i < a.size(); i++) a[i] += o.a[i]; return *this; }
   DenseMatrix& operator*=(T f) { for (T& x : a) x *= f; return *this; }
+  void scale(T f) { for (T& x : a) x *= f; }
   void add(T f, const DenseMatrix& o) { for (size_t i = 0; i < a.size(); i++) a[i] += f * o.a[i]; }
   void right_multiply(const DenseMatrix& B) {   // this <- this * B
     DenseMatrix r(nr, B.nc);
@@ -479,13 +486,24 @@ struct PtrRange {
 
 class BoundaryInfo {
  public:
-  bool has_boundary_id(const Elem*, unsigned short, boundary_id_type) const { return false; }
+  // [upstream] BoundaryInfo: (element, side) -> boundary ids; filled by GmshIO from the lower-dimensional elements of the file
+  // (here: by the wrapper through add_side).  Only SolidSystem::side_time_derivative (solid_system.C:296) asks.
+  std::set<std::tuple<dof_id_type, unsigned short, boundary_id_type>> sides_;
+  std::set<boundary_id_type> ids_;
+  bool has_boundary_id(const Elem* e, unsigned short s, boundary_id_type id) const;
   boundary_id_type boundary_id(const Elem*, unsigned short) const { return -1; }
   void boundary_ids(const Elem*, unsigned short, std::vector<boundary_id_type>& v) const { v.clear(); }
-  std::size_t n_boundary_conds() const { return 0; }
-  void add_side(const Elem*, unsigned short, boundary_id_type) {}
-  const std::set<boundary_id_type>& get_boundary_ids() const { static std::set<boundary_id_type> s; return s; }
+  std::size_t n_boundary_conds() const { return sides_.size(); }
+  void add_side(const Elem* e, unsigned short s, boundary_id_type id);
+  const std::set<boundary_id_type>& get_boundary_ids() const { return ids_; }
 };
+inline bool BoundaryInfo::has_boundary_id(const Elem* e, unsigned short s, boundary_id_type id) const {
+  return sides_.count(std::make_tuple(e->id(), s, id)) != 0;
+}
+inline void BoundaryInfo::add_side(const Elem* e, unsigned short s, boundary_id_type id) {
+  sides_.insert(std::make_tuple(e->id(), s, id));
+  ids_.insert(id);
+}
 
 class MeshBase {
  public:
@@ -618,6 +636,7 @@ class NumericVector {
   void add_vector(const T* d, const std::vector<dof_id_type>& idx) { for (size_t i = 0; i < idx.size(); i++) v[idx[i]] += d[i]; }
   void insert(const std::vector<T>& d, const std::vector<dof_id_type>& idx) { for (size_t i = 0; i < idx.size(); i++) v[idx[i]] = d[i]; }
   void get(const std::vector<dof_id_type>& idx, std::vector<T>& o) const { o.resize(idx.size()); for (size_t i = 0; i < idx.size(); i++) o[i] = v[idx[i]]; }
+  void get(const std::vector<dof_id_type>& idx, T* o) const { for (size_t i = 0; i < idx.size(); i++) o[i] = v[idx[i]]; }
   void close() {}
   bool closed() const { return true; }
   void zero() { std::fill(v.begin(), v.end(), T(0)); }
@@ -865,13 +884,51 @@ typedef TransientSystem<ImplicitSystem> TransientImplicitSystem;
 typedef TransientSystem<ExplicitSystem> TransientExplicitSystem;
 typedef TransientSystem<System> TransientBaseSystem;
 
-// ---- FEMSystem family: declarations only, enough for src/solid_system.h to compile (never run here) ----
+// ---- FEMSystem family: what src/solid_system.{h,C} touch.  FEMContext is a plain holder that the wrapper
+// (ref_solid.cpp) fills per element / side; the Newton driver ([upstream] NewtonSolver) is not modelled. ----
 class DiffContext { public: virtual ~DiffContext() {} };
 class FEBase;
+class QBase;
 class FEMContext : public DiffContext {
  public:
-  template <class... A> void get_element_fe(A&&...) const {}
-  template <class... A> void get_side_fe(A&&...) const {}
+  const Elem* elem_ = nullptr;
+  unsigned char side_ = 0;
+  FEBase* elem_fe_ = nullptr;
+  FEBase* side_fe_ = nullptr;
+  QBase* elem_q_ = nullptr;
+  QBase* side_q_ = nullptr;
+  unsigned nvars_ = 0, ndofs_var_ = 0;
+  DenseVector<Number> residual_;
+  DenseMatrix<Number> jacobian_;
+  std::vector<std::unique_ptr<DenseSubVector<Number>>> sub_res_;
+  std::vector<std::vector<std::unique_ptr<DenseSubMatrix<Number>>>> sub_jac_;
+  Real elem_solution_derivative = 1.0;
+  // [upstream] FEMContext::pre_fe_reinit sizes the element residual/Jacobian variable-major (same order as dof_indices)
+  void resize(unsigned nvars, unsigned ndofs_var) {
+    nvars_ = nvars; ndofs_var_ = ndofs_var;
+    residual_.resize(nvars * ndofs_var);
+    jacobian_.resize(nvars * ndofs_var, nvars * ndofs_var);
+    sub_res_.clear(); sub_jac_.clear();
+    for (unsigned a = 0; a < nvars; a++) {
+      sub_res_.push_back(std::make_unique<DenseSubVector<Number>>(residual_, a * ndofs_var, ndofs_var));
+      sub_jac_.emplace_back();
+      for (unsigned b = 0; b < nvars; b++)
+        sub_jac_.back().push_back(std::make_unique<DenseSubMatrix<Number>>(jacobian_, a * ndofs_var, b * ndofs_var, ndofs_var, ndofs_var));
+    }
+  }
+  const Elem& get_elem() const { return *elem_; }
+  unsigned char get_side() const { return side_; }
+  void get_element_fe(unsigned, FEBase*& fe) const { fe = elem_fe_; }
+  void get_element_fe(unsigned, FEBase*& fe, unsigned char) const { fe = elem_fe_; }
+  void get_side_fe(unsigned, FEBase*& fe) const { fe = side_fe_; }
+  void get_side_fe(unsigned, FEBase*& fe, unsigned char) const { fe = side_fe_; }
+  const QBase& get_element_qrule() const { return *elem_q_; }
+  const QBase& get_side_qrule() const { return *side_q_; }
+  unsigned n_dof_indices(unsigned) const { return ndofs_var_; }
+  DenseSubVector<Number>& get_elem_residual(unsigned v) { return *sub_res_[v]; }
+  DenseSubMatrix<Number>& get_elem_jacobian(unsigned a, unsigned b) { return *sub_jac_[a][b]; }
+  DenseVector<Number>& get_elem_residual() { return residual_; }
+  DenseMatrix<Number>& get_elem_jacobian() { return jacobian_; }
 };
 class DiffSolver {
  public:
@@ -893,6 +950,7 @@ class TimeSolver {
   TimeSolver(DifferentiableSystem&) {}
   virtual ~TimeSolver() {}
   std::unique_ptr<DiffSolver>& diff_solver() { return ds; }
+  virtual void advance_timestep() {}
   std::unique_ptr<DiffSolver> ds;
 };
 class SteadySolver : public TimeSolver { public: using TimeSolver::TimeSolver; };
@@ -921,6 +979,10 @@ class FEMSystem : public DifferentiableSystem {
   void mesh_x_var(unsigned) {}
   void mesh_y_var(unsigned) {}
   void mesh_z_var(unsigned) {}
+  void set_mesh_system(System*) {}
+  void set_mesh_x_var(unsigned) {}
+  void set_mesh_y_var(unsigned) {}
+  void set_mesh_z_var(unsigned) {}
   void postprocess() {}
 };
 
@@ -1036,6 +1098,15 @@ class QBase {
       const Real g = 5.7735026918962576450914878050196e-01;
       const Real p1[2] = {-g, g};
       for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) for (int i = 0; i < 2; i++) { pts[1].push_back(Point(p1[i], p1[j], p1[k])); w[1].push_back(1.0); }
+    } else if (d == 2) {
+      // [upstream] QGauss::init_2D, THIRD: triangles get the 4-point rule with a negative centroid weight
+      // (allow_rules_with_negative_weights defaults to true), quadrilaterals the 2x2 tensor Gauss rule.
+      // Only the side integrals of SolidSystem::side_time_derivative (solid_system.C:273-371) use them.
+      pts[0] = {Point(1. / 3., 1. / 3.), Point(.2, .6), Point(.2, .2), Point(.6, .2)};
+      w[0] = {-27. / 96., 25. / 96., 25. / 96., 25. / 96.};
+      const Real g = 5.7735026918962576450914878050196e-01;
+      const Real p1[2] = {-g, g};
+      for (int j = 0; j < 2; j++) for (int i = 0; i < 2; i++) { pts[1].push_back(Point(p1[i], p1[j])); w[1].push_back(1.0); }
     }
   }
   virtual ~QBase() {}
@@ -1152,8 +1223,51 @@ class FEBase {
       JxW_[p] = jac * q->w_(p);
     }
   }
-  // side quadrature is only reached from dead code in the reference (adpm.C:595 `if (0)`)
-  void reinit(const Elem*, unsigned) { throw std::runtime_error("shim: FEBase::reinit(elem, side) is not implemented"); }
+  // [upstream] FE::reinit(elem, side): quadrature on the side element (TRI3 / QUAD4, q must be a 2-D rule), JxW and xyz
+  // from the side's own map, phi = the PARENT's shape functions at the side points.  libMesh finds the parent reference
+  // point by inverse_map; here it is formed directly from the side's node positions in the parent reference element
+  // (exact; the off-side shape functions are then exactly 0 instead of ~1e-16).  dphi is not filled (not requested by
+  // SolidSystem::init_context).  Node order of a side = [upstream] Tet4/Hex8::side_nodes_map.
+  static const unsigned* side_nodes(ElemType t, unsigned s) {
+    static const unsigned tet[4][4] = {{0, 2, 1, 0}, {0, 1, 3, 0}, {1, 2, 3, 0}, {2, 0, 3, 0}};
+    static const unsigned hex[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+    return t == TET4 ? tet[s] : hex[s];
+  }
+  void reinit(const Elem* e, unsigned side) {
+    const ElemType t = e->type();
+    const unsigned nen = e->n_nodes(), ns = t == TET4 ? 3u : 4u;
+    const unsigned* sn = side_nodes(t, side);
+    q->active = t == TET4 ? 0 : 1;
+    const unsigned nq = q->n_points();
+    phi_.assign(nen, std::vector<Real>(nq, 0.0));
+    dphi_.assign(nen, std::vector<RealGradient>(nq));
+    JxW_.assign(nq, 0.0);
+    xyz_.assign(nq, Point());
+    normals_.assign(nq, Point());
+    for (unsigned p = 0; p < nq; p++) {
+      const Real xi = q->qp(p)(0), eta = q->qp(p)(1);
+      Real N[4], dxi[4], deta[4];
+      if (ns == 3) {
+        N[0] = 1. - xi - eta; N[1] = xi; N[2] = eta;
+        dxi[0] = -1.; dxi[1] = 1.; dxi[2] = 0.; deta[0] = -1.; deta[1] = 0.; deta[2] = 1.;
+      } else {
+        const Real Lx[2] = {.5 * (1. - xi), .5 * (1. + xi)}, Ly[2] = {.5 * (1. - eta), .5 * (1. + eta)}, dL[2] = {-.5, .5};
+        static const int i0[4] = {0, 1, 1, 0}, i1[4] = {0, 0, 1, 1};
+        for (int n = 0; n < 4; n++) { N[n] = Lx[i0[n]] * Ly[i1[n]]; dxi[n] = dL[i0[n]] * Ly[i1[n]]; deta[n] = Lx[i0[n]] * dL[i1[n]]; }
+      }
+      Point x, dxdxi, dxdeta;
+      for (unsigned n = 0; n < ns; n++) {
+        const Point& P = e->point(sn[n]);
+        x.add_scaled(P, N[n]); dxdxi.add_scaled(P, dxi[n]); dxdeta.add_scaled(P, deta[n]);
+        phi_[sn[n]][p] = N[n];
+      }
+      const Point nrm = dxdxi.cross(dxdeta);
+      const Real jac = nrm.norm();   // [upstream] FEMap::compute_face_map: sqrt(g11 g22 - g12 g21) = |dx/dxi x dx/deta|
+      JxW_[p] = jac * q->w_(p);
+      xyz_[p] = x;
+      normals_[p] = nrm / jac;
+    }
+  }
 };
 template <unsigned D, FEFamily F> class FE : public FEBase { public: using FEBase::FEBase; };
 
