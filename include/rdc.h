@@ -47,7 +47,8 @@ extern "C" {
 typedef struct rdc_ctx rdc_ctx;
 
 /* ---- enumerations ---------------------------------------------------------------------------- */
-enum rdc_model { RDC_ADPM = 0, RDC_PIHNA = 1, RDC_RIPF = 2, RDC_PROTEAS = 3, RDC_HCC = 4 };
+enum rdc_model { RDC_ADPM = 0, RDC_PIHNA = 1, RDC_RIPF = 2, RDC_PROTEAS = 3, RDC_HCC = 4,
+                 RDC_SOLID = 5 /* SolidSystem (solid_system.C): unknowns = current node positions x,y,z; see rdc_solid_* below */ };
 enum rdc_elem  { RDC_TET4 = 4, RDC_HEX8 = 8 };
 enum rdc_ksp   { RDC_KSP_GMRES = 0, RDC_KSP_CG = 1, RDC_KSP_BICGSTAB = 2 };
 enum rdc_pc    { RDC_PC_JACOBI = 0, RDC_PC_NONE = 1, RDC_PC_BJACOBI = 2 /* reserved (v x v nodal block): RDC_E_ARG today */ };
@@ -223,6 +224,45 @@ struct rdc_range_cond { double w[5]; double div, lo, hi; };
 int rdc_set_subdomains(rdc_ctx*, const int32_t* region /* [n_elems] or NULL */, int n_regions);
 int rdc_region_volumes(rdc_ctx*, int ncond, const struct rdc_range_cond* cond, double* vol /* [n_regions] */);
 int rdc_region_last_mean(rdc_ctx*, int var, double* mean /* [n_regions] */);
+
+/* ---- solid mechanics: SolidSystem of solid_system.C / solid.C / coupled_hcc.C:117-132 -----------
+ * A context created with model RDC_SOLID holds the CURRENT node positions as its solution (rdc_set_solution /
+ * rdc_get_solution, dof = 3*node + d unless node_dof_base says otherwise) -- solid.C:27-30, mesh_position_get/set.  One GPU
+ * per context.  The Krylov solvers of rdc_solve (ksp) with point Jacobi solve the Newton systems.
+ *   rdc_solid_set_reference  <- SolidSystem::save_initial_mesh (solid_system.C:26-48): undeformed positions [n_nodes*3]
+ *   rdc_solid_set_materials  <- es.parameters "material/<id>/Hyperelastic/{Young,Poisson,FibreStiffness,
+ *                               VolumetricStretchRatio/rate_0..2}" (solid.C:276-291, read at solid_system.C:182-189):
+ *                               mats[nmat*6] in that order, mat_of[n_elems] = index of elem->subdomain_id() in the table
+ *   rdc_solid_set_fibres     <- "SolidSystem::fibre" variables 0-2 (solid.C:303-337, solid_system.C:205-213): [n_elems*3] or NULL
+ *   rdc_solid_set_bcs        <- "BCs", "BC/<id>/displacement", "BCs/displacement_penalty" + BoundaryInfo::has_boundary_id
+ *                               (solid_system.C:288-304): side k = libMesh side side_no[k] of element side_elem[k] carries
+ *                               condition side_bc[k]; bc_disp[nbc*3], NaN = component left free
+ *   rdc_solid_assemble       <- [upstream] FEMSystem::assembly(true, true): element_time_derivative + side_time_derivative
+ *                               (solid_system.C:146-371) -> Jacobian (rdc_download_csr) and residual (rdc_get_rhs)
+ *   rdc_solid_newton         <- SolidSystem::run_solver (solid_system.C:373-392) = [upstream] NewtonSolver::solve configured by
+ *                               solid_system.C:80-98; opts = {max_nonlinear_iterations, relative_step_tolerance,
+ *                               relative_residual_tolerance, absolute_residual_tolerance, require_reduction,
+ *                               max_linear_iterations, initial_linear_tolerance}; info[4] = {newton iterations, linear
+ *                               iterations, final residual norm, converged 0/1}
+ *   rdc_solid_post_process   <- SolidSystem::post_process (solid_system.C:394-538): per element mean normal stress
+ *                               ("SolidSystem::pressure"), von Mises stress, current fibre vector; outputs may be NULL */
+int rdc_solid_set_reference(rdc_ctx*, const double* xyz_undeformed /* [n_nodes*3] */);
+int rdc_solid_set_materials(rdc_ctx*, int nmat, const double* mats /* [nmat*6] */, const int32_t* mat_of /* [n_elems] or NULL */);
+int rdc_solid_set_fibres(rdc_ctx*, const double* fibres /* [n_elems*3] or NULL */);
+int rdc_solid_set_bcs(rdc_ctx*, int nbc, const double* bc_disp /* [nbc*3] */, int64_t nside, const int64_t* side_elem,
+                      const int32_t* side_no, const int32_t* side_bc, double penalty);
+int rdc_solid_assemble(rdc_ctx*, double pseudo_time);
+int rdc_solid_newton(rdc_ctx*, double pseudo_time, const double* opts /* [7] */, int ksp, double* info /* [4] */);
+int rdc_solid_post_process(rdc_ctx*, double pseudo_time, double* press, double* von_mises, double* fibre_current);
+/* host-only probes of the element arithmetic (no device needed; the CPU tests hold them to the oracle): row li of the element
+ * residual/tangent R[3], K[9*nen] (plane a*3+c, column node j at (a*3+c)*nen + j); the penalty row of node i of a side with
+ * ns nodes R[3], Kd[ns*3]; post_process of one element out[5] = {p, von Mises, fibre[3]} */
+int rdc_solid_probe_row(int elem_type, const double* x_cur, const double* x_und, const double* mat6, double pseudo_time,
+                        const double* eta, int li, double* R, double* K);
+int rdc_solid_probe_bc_row(int ns, const double* x_cur, const double* x_und, const double* disp, double pseudo_time, double penalty,
+                           int i, double* R, double* Kd);
+int rdc_solid_probe_post(int elem_type, const double* x_cur, const double* x_und, const double* mat6, double pseudo_time,
+                         const double* eta, double* out5);
 
 /* read-only streaming probe over the stored operator values (reference point for the SpMV roofline): mean ms, bytes */
 int rdc_bench_stream(rdc_ctx*, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes);

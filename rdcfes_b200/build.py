@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "librdcgpu.so")
-SOURCES = ["api.cu", "assemble.cu", "solver.cu", "p2p.cu", "reduce.cu", "setup.cpp", "comm.cpp"]
-HEADERS = ["rdc_internal.h", "models.cuh", "p2p_dev.cuh", os.path.join("..", "..", "include", "rdc.h")]
+SOURCES = ["api.cu", "assemble.cu", "solver.cu", "solid.cu", "p2p.cu", "reduce.cu", "setup.cpp", "comm.cpp"]
+HEADERS = ["rdc_internal.h", "models.cuh", "asm_common.cuh", "solid_dev.cuh", "p2p_dev.cuh", os.path.join("..", "..", "include", "rdc.h")]
 
 
 def _nvcc() -> str:

@@ -46,7 +46,7 @@ extern "C" const char* rdc_version(void) { return "rdcfes_b200 0.1 (sm_100a)"; }
 
 extern "C" int rdc_model_nvars(int model) {
   switch (model) {
-    case RDC_ADPM: case RDC_RIPF: case RDC_HCC: return 3;
+    case RDC_ADPM: case RDC_RIPF: case RDC_HCC: case RDC_SOLID: return 3;
     case RDC_PIHNA: case RDC_PROTEAS: return 5;
   }
   return -1;
@@ -58,6 +58,7 @@ extern "C" int rdc_model_nparams(int model) {
     case RDC_RIPF: return RIPF_NPARAMS;
     case RDC_PROTEAS: return PROTEAS_NPARAMS;
     case RDC_HCC: return HCC_NPARAMS;
+    case RDC_SOLID: return 0;   // materials and boundary conditions go through rdc_solid_set_*
   }
   return -1;
 }
@@ -93,6 +94,7 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     g_create_err = "rdc_create: cudaGetDevice failed";
     return RDC_E_NODEVICE;
   }
+  if (model == RDC_SOLID && nranks > 1) { g_create_err = "rdc_create_distributed: the solid path runs on one GPU per context"; return RDC_E_ARG; }
   rdc_ctx* c = new (std::nothrow) rdc_ctx();
   if (!c) return RDC_E_NOMEM;
   c->model = model; c->etype = elem_type; c->nen = elem_type == RDC_TET4 ? 4 : 8; c->nv = nv;
@@ -251,6 +253,7 @@ extern "C" void rdc_destroy(rdc_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   solver_free(c);
   region_free(c);
+  solid_free(c);
   if (p2p_owns(c, c->d_u)) c->d_u = nullptr;
   if (p2p_owns(c, c->d_td)) c->d_td = nullptr;
   comm_destroy(c);
@@ -478,6 +481,7 @@ static void resolve_timings(rdc_ctx* c, bool wait) {
 
 extern "C" int rdc_assemble(rdc_ctx* c, double time, double dt) {
   CHECK_CTX(c);
+  if (c->model == RDC_SOLID) { c->err = "rdc_assemble: use rdc_solid_assemble / rdc_solid_newton on a solid context"; return RDC_E_STATE; }
   if (!c->have_params) { c->err = "rdc_assemble: rdc_set_params has not been called"; return RDC_E_STATE; }
   if (!(dt > 0.0)) { c->err = "rdc_assemble: dt must be positive"; return RDC_E_ARG; }
   c->time = time; c->dt = dt;
@@ -516,6 +520,7 @@ extern "C" int rdc_solve(rdc_ctx* c, int ksp, int pc, double rtol, int maxits, i
 
 extern "C" int rdc_clamp(rdc_ctx* c) {
   CHECK_CTX(c);
+  if (c->model == RDC_SOLID) { c->err = "rdc_clamp: node positions are not clamped (no check_solution in solid_system.C)"; return RDC_E_STATE; }
   if (c->model == RDC_RIPF) {
     if (!c->have_params || !c->d_rt) { c->err = "rdc_clamp (RIPF): parameters and RT dose field are required"; return RDC_E_STATE; }
     if (!(c->dt > 0.0)) { c->err = "rdc_clamp (RIPF): time step unknown; call rdc_assemble/rdc_step or rdc_set_dt first"; return RDC_E_STATE; }

@@ -92,6 +92,7 @@ void bucket_regions(int64_t E_loc, const uint8_t* counted, const int32_t* region
 
 struct SolverWork;  // solver.cu
 struct RegionWork;  // reduce.cu
+struct SolidWork;   // solid.cu
 
 // Tuning switches of one context.  Defaults come from the environment (RDC_<NAME> upper case) at rdc_create and
 // can be changed with rdc_set_option; the parity tests use them to run the alternative kernels side by side.
@@ -159,6 +160,7 @@ struct rdc_ctx {
   // solver
   SolverWork* work = nullptr;
   RegionWork* region = nullptr;      // save_solution reductions (rdc_set_subdomains)
+  SolidWork* solid = nullptr;        // RDC_SOLID: reference configuration, materials, boundary conditions (solid.cu)
 
   // comm
   rdc::P2P* p2p = nullptr;
@@ -205,6 +207,8 @@ int region_setup(rdc_ctx* c, const int32_t* region, int n_regions);
 void region_free(rdc_ctx* c);
 int region_volumes(rdc_ctx* c, int ncond, const rdc_range_cond* cond, double* vol);
 int region_last_mean(rdc_ctx* c, int var, double* mean);
+// solid.cu
+void solid_free(rdc_ctx* c);
 // comm.cpp
 int comm_unique_id(void* out128, std::string& err);
 int comm_init(rdc_ctx* c, const void* uid, std::string& err);

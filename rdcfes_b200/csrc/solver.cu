@@ -557,10 +557,11 @@ static void spmv_mode(int minb, int mode, unsigned grid, cudaStream_t st, int n,
 // depend on the model code; create_impl checks them against assemble.cu's model_kmask()
 static constexpr unsigned KM_ADPM = 0x15F, KM_RIPF = 0x1F7, KM_HCC = 0x1DF;
 static constexpr unsigned KM_PIHNA = 0x1EFBDEF, KM_PROTEAS = 0x127BDEF;
+static constexpr unsigned KM_SOLID = 0x1FF;   // dense 3 x 3 node block of the solid-mechanics Jacobian (solid.cu)
 
 int spmv_masks_ok() {
   return model_kmask(RDC_ADPM) == KM_ADPM && model_kmask(RDC_RIPF) == KM_RIPF && model_kmask(RDC_HCC) == KM_HCC &&
-         model_kmask(RDC_PIHNA) == KM_PIHNA && model_kmask(RDC_PROTEAS) == KM_PROTEAS;
+         model_kmask(RDC_PIHNA) == KM_PIHNA && model_kmask(RDC_PROTEAS) == KM_PROTEAS && model_kmask(RDC_SOLID) == KM_SOLID;
 }
 
 template <int NV, unsigned KMASK, int STAGES>
@@ -631,6 +632,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
       case RDC_RIPF: trc = RDC_TMA_MODEL(3, KM_RIPF, 2); break;
       case RDC_HCC: trc = RDC_TMA_MODEL(3, KM_HCC, 2); break;
       case RDC_PIHNA: trc = RDC_TMA_MODEL(5, KM_PIHNA, 2); break;
+      case RDC_SOLID: trc = RDC_TMA_MODEL(3, KM_SOLID, 2); break;
       default: trc = RDC_TMA_MODEL(5, KM_PROTEAS, 2); break;
     }
 #undef RDC_TMA_MODEL
@@ -642,6 +644,7 @@ static int spmv(rdc_ctx* c, int mode, const double* x, double* y, const double* 
       case RDC_RIPF: RDC_SPMV_MODEL(3, KM_RIPF); break;
       case RDC_HCC: RDC_SPMV_MODEL(3, KM_HCC); break;
       case RDC_PIHNA: RDC_SPMV_MODEL(5, KM_PIHNA); break;
+      case RDC_SOLID: RDC_SPMV_MODEL(3, KM_SOLID); break;
       default: RDC_SPMV_MODEL(5, KM_PROTEAS); break;
     }
 #undef RDC_SPMV_MODEL
@@ -2160,6 +2163,7 @@ static int bicgstab_persist_begin(rdc_ctx* c, const double* scale, double rtol, 
     case RDC_RIPF: rc = persist_launch<3, KM_RIPF>(c, A); break;
     case RDC_HCC: rc = persist_launch<3, KM_HCC>(c, A); break;
     case RDC_PIHNA: rc = persist_launch<5, KM_PIHNA>(c, A); break;
+    case RDC_SOLID: rc = persist_launch<3, KM_SOLID>(c, A); break;
     default: rc = persist_launch<5, KM_PROTEAS>(c, A); break;
   }
   if (rc) return rc;

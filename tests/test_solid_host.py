@@ -1,0 +1,65 @@
+"""The element arithmetic of the CUDA solid path (rdcfes_b200/csrc/solid_dev.cuh) compiled for the host and held to the
+CPU oracle (CPU only, no device): the closed-form tangent row, the penalty row and post_process of one element.  The
+kernels of solid.cu call exactly these functions; the GPU tests (test_gpu_solid.py) then cover staging and assembly."""
+import numpy as np
+import pytest
+
+import solid_cases as SC
+from oracle import solid as S
+from rdcfes_b200 import solid as G
+
+
+@pytest.mark.parametrize("et", [SC.TET4, SC.HEX8])
+def test_tangent_rows_match_oracle(et):
+    c = SC.general_case(et, penalty=0.0)
+    x = SC.perturbed(c)
+    orc = S.OracleSolid(c)
+    nen = c.conn.shape[1]
+    worst_r = worst_k = 0.0
+    for e in range(c.E):
+        Ro, Ko = orc.element(e, x, 0.3)
+        Ko = Ko.reshape(3, nen, 3, nen)                     # variable-major: (a, i, c, j)
+        nodes = c.conn[e]
+        for li in range(nen):
+            R, K = G.probe_row(et, x[nodes], c.xund[nodes], c.mats[c.mat_of[e]], 0.3, c.fibres[e], li)
+            worst_r = max(worst_r, np.abs(R - Ro.reshape(3, nen)[:, li]).max() / np.abs(Ro).max())
+            worst_k = max(worst_k, np.abs(K - Ko[:, li, :, :]).max() / np.abs(Ko).max())
+    assert worst_r <= 1e-12 and worst_k <= 1e-12, (worst_r, worst_k)
+
+
+@pytest.mark.parametrize("et", [SC.TET4, SC.HEX8])
+def test_penalty_rows_match_oracle(et):
+    c = SC.general_case(et, penalty=1.0e5)
+    x = SC.perturbed(c)
+    nen = c.conn.shape[1]
+    se, sn, sb, bd = c.arrays()
+    L = S.O.lib()
+    import ctypes as C
+    for k in range(se.shape[0]):
+        nodes = c.conn[se[k]]
+        Xc, Xu = np.ascontiguousarray(x[nodes]), np.ascontiguousarray(c.xund[nodes])
+        Re, Ke = np.zeros(3 * nen), np.zeros((3 * nen, 3 * nen))
+        disp = np.ascontiguousarray(bd[sb[k]])
+        assert L.orc_solid_side(C.c_int(et), C.c_int(int(sn[k])), S._p(Xc), S._p(Xu), S._p(disp), C.c_double(0.3), C.c_double(c.penalty),
+                                C.c_int(1), S._p(Re), S._p(Ke)) == 0
+        Ke = Ke.reshape(3, nen, 3, nen)
+        loc = S.SIDE_NODES[et][sn[k]]
+        for i, li in enumerate(loc):
+            R, Kd = G.probe_bc_row(len(loc), Xc[list(loc)], Xu[list(loc)], disp, 0.3, c.penalty, i)
+            assert np.abs(R - Re.reshape(3, nen)[:, li]).max() <= 1e-12 * np.abs(Re).max()
+            for j, lj in enumerate(loc):
+                for d in range(3):
+                    assert abs(Kd[j, d] - Ke[d, li, d, lj]) <= 1e-12 * np.abs(Ke).max()
+
+
+@pytest.mark.parametrize("et", [SC.TET4, SC.HEX8])
+def test_post_process_matches_oracle(et):
+    c = SC.general_case(et)
+    x = SC.perturbed(c)
+    po, vo, fo = S.OracleSolid(c).post(x, 0.4)
+    scale = np.abs(po).max() + vo.max()
+    for e in range(c.E):
+        nodes = c.conn[e]
+        out = G.probe_post(et, x[nodes], c.xund[nodes], c.mats[c.mat_of[e]], 0.4, c.fibres[e])
+        assert abs(out[0] - po[e]) <= 1e-12 * scale and abs(out[1] - vo[e]) <= 1e-12 * scale
+        assert np.abs(out[2:] - fo[e]).max() <= 1e-13
