@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <fstream>
 #include <map>
 #include <memory>
@@ -75,6 +76,10 @@ struct Mesh {
   std::vector<double> xyz;       // [N*3]
   std::vector<int32_t> conn;     // [E*nen], 0-based
   std::vector<int> subdomain;    // [E] first Gmsh tag (physical id) == libMesh subdomain_id
+  // lower-dimensional elements of the file (TRI3 / QUAD4): [upstream] GmshIO turns their physical tag into the boundary id of
+  // the volume-element side with the same nodes (BoundaryInfo::add_side) -- what SolidSystem::side_time_derivative asks for
+  std::vector<std::array<int32_t, 4>> bface;   // node ids, -1 padded
+  std::vector<int> btag;
 };
 
 // Gmsh 2.2 ASCII as written by process_mesh.C:22-83; volume elements only (4 = TET4, 5 = HEX8), file order
@@ -106,6 +111,17 @@ static Mesh read_gmsh(const std::string& path) {
         ss >> id >> type >> ntags;
         std::vector<long> tags((size_t)ntags);
         for (auto& t : tags) ss >> t;
+        if (type == 2 || type == 3) {   // 3-node triangle / 4-node quadrangle
+          std::array<int32_t, 4> f = {-1, -1, -1, -1};
+          for (int l = 0; l < (type == 2 ? 3 : 4); l++) {
+            long v;
+            ss >> v;
+            f[l] = id2idx.at(v);
+          }
+          m.bface.push_back(f);
+          m.btag.push_back(ntags > 0 ? (int)tags[0] : 0);
+          continue;
+        }
         const int nen = type == 4 ? 4 : (type == 5 ? 8 : 0);
         if (!nen) continue;
         if (m.nen && m.nen != nen) die("mixed volume element types");
@@ -165,6 +181,167 @@ static std::vector<double> flat_params(const ParamKey (&table)[NK], const Input&
   return p;
 }
 
+
+// ---- solid mechanics (solid.C, solid_system.C; the other half of coupled_hcc.C) --------------------------------------
+// Everything solid.C:input() / coupled_hcc.C:input() read for the SolidSystem, handed to a RDC_SOLID context.
+struct SolidModel {
+  rdc_ctx* ctx = nullptr;
+  double opts[7];        // rdc_solid_newton: solver/nonlinear/*, solver/linear/* (solid.C:226-245)
+  double pseudo_time = 0.0;
+};
+
+static SolidModel make_solid(const Input& in, const Mesh& mesh, const std::string& dir) {
+  SolidModel sm;
+  const int64_t N = (int64_t)mesh.xyz.size() / 3, E = (int64_t)mesh.conn.size() / mesh.nen;
+  auto ck = [&](int rc, const char* what) {
+    if (rc) die(std::string(what) + ": " + rdc_last_error(sm.ctx));
+  };
+  if (in.integer("solver/assembly_use_symmetry", 0) || in.str("solver/assembly_use_symmetry", "false") == "true")
+    die("solver/assembly_use_symmetry = true (mirrored upper triangle, solid_system.C:248-262) is not offered by the device path");
+  ck(rdc_create(&sm.ctx, RDC_SOLID, mesh.nen, N, E, mesh.conn.data(), mesh.xyz.data(), nullptr, -1), "rdc_create(solid)");
+  ck(rdc_set_solution(sm.ctx, mesh.xyz.data()), "rdc_set_solution");            // mesh_position_get (solid_system.C:82)
+  ck(rdc_solid_set_reference(sm.ctx, mesh.xyz.data()), "rdc_solid_set_reference");   // save_initial_mesh (solid.C:68)
+  // materials = the subdomain ids that carry parameters (solid.C:273-291); every element's subdomain must be one of them
+  const std::set<int> mat_ids = integers_of(in.str("materials", " 0 "));
+  std::map<int, int> mat_index;
+  std::vector<double> mats;
+  for (int id : mat_ids) {
+    const std::string k = "material/" + std::to_string(id) + "/Hyperelastic/";
+    mat_index.emplace(id, (int)mat_index.size());
+    mats.push_back(in.real(k + "Young", 1.0e3));
+    mats.push_back(in.real(k + "Poisson", 0.3));
+    mats.push_back(in.real(k + "FibreStiffness", 0.0));
+    for (int d = 0; d < 3; d++) mats.push_back(in.real(k + "VolumetricStretchRatio/rate_" + std::to_string(d), 0.0));
+  }
+  std::vector<int32_t> mat_of((size_t)E);
+  for (int64_t e = 0; e < E; e++) {
+    auto it = mat_index.find(mesh.subdomain[e]);
+    if (it == mat_index.end())
+      die("element subdomain " + std::to_string(mesh.subdomain[e]) + " has no material/<id>/Hyperelastic parameters (solid_system.C:182)");
+    mat_of[e] = it->second;
+  }
+  ck(rdc_solid_set_materials(sm.ctx, (int)mat_ids.size(), mats.data(), mat_of.data()), "rdc_solid_set_materials");
+  const std::string fib = in.str("input_fibres", ".");
+  if (fib != ".") {   // solid.C:303-337: one direction per element, normalised
+    std::vector<double> f = read_table(dir + fib, (size_t)E, 3);
+    for (int64_t e = 0; e < E; e++) {
+      const double m = sqrt(f[3 * e] * f[3 * e] + f[3 * e + 1] * f[3 * e + 1] + f[3 * e + 2] * f[3 * e + 2]);
+      if (m <= 1.0e-6) die("input_fibres: zero fibre vector (solid.C:319)");
+      for (int d = 0; d < 3; d++) f[3 * e + d] /= m;
+    }
+    ck(rdc_solid_set_fibres(sm.ctx, f.data()), "rdc_solid_set_fibres");
+  }
+  // boundary conditions: "BCs" ids, BC/<id>/displacement/<d> (NAN = free), penalty (solid.C:247-266)
+  const std::set<int> bc_ids = integers_of(in.str("BCs", " 0 "));
+  std::map<int, int> bc_index;
+  std::vector<double> bc_disp;
+  for (int id : bc_ids) {
+    bc_index.emplace(id, (int)bc_index.size());
+    for (int d = 0; d < 3; d++) bc_disp.push_back(in.real("BC/" + std::to_string(id) + "/displacement/" + std::to_string(d), 0.0));
+  }
+  // sides: the volume-element side with the nodes of each tagged boundary face ([upstream] side_nodes_map)
+  static const int tet[4][4] = {{0, 2, 1, -1}, {0, 1, 3, -1}, {1, 2, 3, -1}, {2, 0, 3, -1}};
+  static const int hex[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+  const int ns = mesh.nen == 4 ? 3 : 4, nsides = mesh.nen == 4 ? 4 : 6;
+  std::map<std::array<int32_t, 4>, std::pair<int64_t, int>> wanted;   // sorted nodes of a tagged face -> slot
+  std::vector<std::array<int32_t, 4>> keys(mesh.bface.size());
+  for (size_t k = 0; k < mesh.bface.size(); k++) {
+    if (!bc_index.count(mesh.btag[k])) continue;
+    std::array<int32_t, 4> key = mesh.bface[k];
+    std::sort(key.begin(), key.begin() + ns);
+    keys[k] = key;
+    wanted.emplace(key, std::make_pair((int64_t)-1, -1));
+  }
+  for (int64_t e = 0; e < E && !wanted.empty(); e++)
+    for (int sd = 0; sd < nsides; sd++) {
+      std::array<int32_t, 4> key = {-1, -1, -1, -1};
+      for (int j = 0; j < ns; j++) key[j] = mesh.conn[(size_t)e * mesh.nen + (mesh.nen == 4 ? tet[sd][j] : hex[sd][j])];
+      std::sort(key.begin(), key.begin() + ns);
+      auto it = wanted.find(key);
+      if (it != wanted.end() && it->second.first < 0) it->second = {e, sd};
+    }
+  std::vector<int64_t> side_elem;
+  std::vector<int32_t> side_no, side_bc;
+  for (size_t k = 0; k < mesh.bface.size(); k++) {
+    if (!bc_index.count(mesh.btag[k])) continue;
+    const auto& hit = wanted.at(keys[k]);
+    if (hit.first < 0) die("a tagged boundary face of the mesh is not a side of any volume element");
+    side_elem.push_back(hit.first); side_no.push_back(hit.second); side_bc.push_back(bc_index.at(mesh.btag[k]));
+  }
+  ck(rdc_solid_set_bcs(sm.ctx, (int)bc_ids.size(), bc_disp.data(), (int64_t)side_elem.size(), side_elem.data(), side_no.data(),
+                       side_bc.data(), in.real("BCs/displacement_penalty", 1.0e5)), "rdc_solid_set_bcs");
+  sm.opts[0] = in.integer("solver/nonlinear/max_nonlinear_iterations", 100);
+  sm.opts[1] = in.real("solver/nonlinear/relative_step_tolerance", 1.0e-3);
+  sm.opts[2] = in.real("solver/nonlinear/relative_residual_tolerance", 1.0e-8);
+  sm.opts[3] = in.real("solver/nonlinear/absolute_residual_tolerance", 1.0e-8);
+  sm.opts[4] = in.str("solver/nonlinear/require_reduction", "false") == "true" ? 1.0 : 0.0;
+  sm.opts[5] = in.integer("solver/linear/max_linear_iterations", 50000);
+  sm.opts[6] = in.real("solver/linear/initial_linear_tolerance", 1.0e-3);
+  printf("solid: %lld elements, %zu materials, %zu boundary conditions on %zu sides\n", (long long)E, mat_ids.size(), bc_ids.size(), side_elem.size());
+  return sm;
+}
+
+// SolidSystem::run_solver + post_process (solid.C:96-99, coupled_hcc.C:117-124) at the model's pseudo-time
+static void solid_load_step(SolidModel& sm, int ksp, std::vector<double>* press, std::vector<double>* vm) {
+  double info[4] = {0, 0, 0, 0};
+  if (rdc_solid_newton(sm.ctx, sm.pseudo_time, sm.opts, ksp, info)) die(std::string("rdc_solid_newton: ") + rdc_last_error(sm.ctx));
+  printf("  solid: pseudo-time %g, %d Newton iterations, %d linear iterations, residual %.3e%s\n", sm.pseudo_time, (int)info[0], (int)info[1],
+         info[2], info[3] != 0.0 ? "" : "  (NOT converged)");
+  if (press && vm && rdc_solid_post_process(sm.ctx, sm.pseudo_time, press->data(), vm->data(), nullptr))
+    die(std::string("rdc_solid_post_process: ") + rdc_last_error(sm.ctx));
+}
+
+// -m solid: the driver of solid.C:14-112
+static int run_solid(const Input& in, const std::string& dir, int ksp, bool vtu_binary, const std::string& sol_out) {
+  Mesh mesh = read_gmsh(dir + in.str("input_GMSH", "input.msh"));
+  const int64_t N = (int64_t)mesh.xyz.size() / 3, E = (int64_t)mesh.conn.size() / mesh.nen;
+  SolidModel sm = make_solid(in, mesh, dir);
+  const double loading_step = in.real("loading_step", 1.0);
+  const int n_load = (int)(1.0 / loading_step);                                  // solid.C:166-167
+  const int out_step = in.integer("output_step", 0);
+  std::set<int> out_points;
+  if (out_step > 0) for (int l = out_step; l <= n_load; l += out_step) out_points.insert(l);
+  else out_points.insert(n_load);                                                // solid.C:171-177 ("output_time_points" of the file is not read)
+  if (in.integer("remeshing_step", 0) > 0 && in.integer("remeshing_step", 0) <= n_load && in.integer("mesh/AMR/max_steps", 0) > 0)
+    die("remeshing_step asks for adaptive mesh refinement (solid.C:102-103, 339-369), which this driver does not do");
+  std::unique_ptr<PvdCollection> pvd;
+  if (in.kv.count("output_PARAVIEW")) pvd.reset(new PvdCollection(dir + in.str("output_PARAVIEW", "output4paraview"), vtu_binary));
+  const std::vector<std::string> names = {"x", "y", "z", "undeformed_x", "undeformed_y", "undeformed_z", "u_x", "u_y", "u_z"};   // solid.C:27-44
+  std::vector<double> x((size_t)N * 3), vals((size_t)N * 9), press((size_t)E), vm((size_t)E);
+  auto update_pvd = [&](unsigned l) {
+    if (!pvd) return;
+    if (rdc_get_solution(sm.ctx, x.data())) die("rdc_get_solution");
+    for (int64_t n = 0; n < N; n++)
+      for (int d = 0; d < 3; d++) {
+        vals[(size_t)n * 9 + d] = x[(size_t)n * 3 + d];
+        vals[(size_t)n * 9 + 3 + d] = mesh.xyz[(size_t)n * 3 + d];
+        vals[(size_t)n * 9 + 6 + d] = x[(size_t)n * 3 + d] - mesh.xyz[(size_t)n * 3 + d];
+      }
+    const VtuMesh vmesh = {mesh.nen, &x, &mesh.conn, &mesh.subdomain, nullptr};   // the moved mesh, as Paraview_IO sees it
+    if (!pvd->add(vmesh, names, vals, l)) die("cannot write the .vtu file");
+  };
+  update_pvd(0);
+  for (int l = 1; l <= n_load; l++) {
+    sm.pseudo_time += loading_step;
+    printf(" ==== Step %4d out of %4d (pseudo-time=%g) ====\n", l, n_load, sm.pseudo_time);
+    solid_load_step(sm, ksp, &press, &vm);
+    if (out_points.count(l)) update_pvd((unsigned)l);
+  }
+  if (!sol_out.empty()) {   // final positions, then pressure and von Mises stress per element
+    if (rdc_get_solution(sm.ctx, x.data())) die("rdc_get_solution");
+    FILE* f = fopen(sol_out.c_str(), "wb");
+    if (!f || fwrite(x.data(), sizeof(double), x.size(), f) != x.size() || fwrite(press.data(), sizeof(double), press.size(), f) != press.size() ||
+        fwrite(vm.data(), sizeof(double), vm.size(), f) != vm.size())
+      die("cannot write " + sol_out);
+    fclose(f);
+  }
+  rdc_stats st;
+  rdc_get_stats(sm.ctx, &st);
+  printf("done: %d load steps, %lld kernel launches\n", n_load, (long long)st.kernel_launches);
+  rdc_destroy(sm.ctx);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   std::string model_name = "adpm", in_path, sol_out;
   int ksp = RDC_KSP_BICGSTAB;
@@ -179,7 +356,11 @@ int main(int argc, char** argv) {
     else in_path = argv[a];
   }
   if (in_path.empty())
-    die("usage: rdc_driver -m adpm|pihna|ripf|proteas|coupled_hcc <input.dat> [ksp=2] [vtu=binary] [solid=off] [solution_out=file]");
+    die("usage: rdc_driver -m adpm|pihna|ripf|proteas|coupled_hcc|solid <input.dat> [ksp=2] [vtu=binary] [solid=off] [solution_out=file]");
+  if (model_name == "solid") {
+    const size_t sl = in_path.find_last_of('/');
+    return run_solid(Input(in_path), sl == std::string::npos ? std::string() : in_path.substr(0, sl + 1), ksp, vtu_binary, sol_out);
+  }
   const int model = model_name == "adpm" ? RDC_ADPM : model_name == "pihna" ? RDC_PIHNA : model_name == "ripf" ? RDC_RIPF
                   : model_name == "proteas" ? RDC_PROTEAS : (model_name == "coupled_hcc" || model_name == "hcc") ? RDC_HCC : -1;
   if (model < 0) die("unknown model " + model_name + " (main.C:24-38 knows adpm, pihna, proteas, ripf; coupled_hcc.C is the fifth)");
@@ -210,10 +391,6 @@ int main(int argc, char** argv) {
   else out_points = integers_of(in.str("output_time_points", std::to_string(n_steps)));
   if (model == RDC_PROTEAS && in.integer("refinement_step", n_steps + 1) <= n_steps)
     die("refinement_step <= time_step_number asks for adaptive mesh refinement (proteas.C:82-83), which this driver does not do");
-  if (model == RDC_HCC && !rdc_only)
-    die("coupled_hcc.C:117-132 solves the solid-mechanics equilibrium at the loading time points and moves the mesh; that path is "
-        "not part of this driver.  Pass solid=off to run the reaction-diffusion system on the fixed mesh (no loading steps).");
-
   // ---- mesh and initial fields ---------------------------------------------------------------------------------
   Mesh mesh = read_gmsh(dir + in.str("input_GMSH", "input.msh"));
   const int64_t N = (int64_t)mesh.xyz.size() / 3, E = (int64_t)mesh.conn.size() / mesh.nen;
@@ -224,6 +401,18 @@ int main(int argc, char** argv) {
   std::vector<int32_t> region((size_t)E);
   for (int64_t e = 0; e < E; e++) region[e] = reg_of[mesh.subdomain[e]];
   const int n_regions = model == RDC_ADPM ? (int)parcellation.size() : 1;   // only ADPM reports per region
+  // coupled_hcc.C:39-74,117-132: the SolidSystem on the same mesh, solved at the loading time points; it moves the mesh
+  const bool with_solid = model == RDC_HCC && !rdc_only;
+  SolidModel solid;
+  std::set<int> load_points;
+  double loading_step = 0.0;
+  if (with_solid) {
+    solid = make_solid(in, mesh, dir);
+    const int n_load = in.integer("number_of_loading_steps", 1);
+    if (n_load < 1 || n_steps % n_load) die("number_of_time_steps must be a multiple of number_of_loading_steps (coupled_hcc.C:204-208)");
+    loading_step = dt * n_steps / n_load;                                       // coupled_hcc.C:194-197
+    for (int t = n_steps / n_load; t <= n_steps; t += n_steps / n_load) load_points.insert(t);
+  }
 
   // ---- hand-over (once) -------------------------------------------------------------------------------------------
   rdc_ctx* ctx = nullptr;
@@ -344,11 +533,19 @@ int main(int argc, char** argv) {
   long its_total = 0;
   for (int t = 1; t <= n_steps; t++) {
     time += dt;
+    if (with_solid && load_points.count(t)) solid.pseudo_time += loading_step;   // coupled_hcc.C:100-101
     int its = 0;
     double res = 0;
     ck(rdc_step(ctx, time, dt, ksp, RDC_PC_JACOBI, 1e-12, 5000, 30, &its, &res), "rdc_step");
     its_total += its;
     printf(" ==== Step %4d out of %4d (Time=%9g) ==== its %d res %.3e\n", t, n_steps, time, its, res);
+    if (with_solid && load_points.count(t)) {   // coupled_hcc.C:117-128: equilibrium, then the mesh both systems share has moved
+      solid_load_step(solid, ksp, nullptr, nullptr);
+      std::vector<double> x((size_t)N * 3);
+      if (rdc_get_solution(solid.ctx, x.data())) die("rdc_get_solution(solid)");
+      ck(rdc_update_coords(ctx, x.data()), "rdc_update_coords");
+      mesh.xyz = x;                                                              // ParaView output shows the moved mesh
+    }
     if (out_points.count(t)) { save_solution(time); update_pvd((unsigned)t); }
   }
   if (!sol_out.empty()) {
@@ -362,5 +559,6 @@ int main(int argc, char** argv) {
   rdc_get_stats(ctx, &st);
   printf("done: %d steps, %ld Krylov iterations, %lld kernel launches\n", n_steps, its_total, (long long)st.kernel_launches);
   rdc_destroy(ctx);
+  if (with_solid) rdc_destroy(solid.ctx);
   return 0;
 }

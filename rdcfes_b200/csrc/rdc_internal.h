@@ -110,7 +110,7 @@ struct rdc_options {
                                // iteration), -1 automatic: when a CTA of the resident grid gets at most 40 operator tiles per SpMV
   int persist_timing = 1;      // the persistent solver times its phases (SpMV time of rdc_stats); 0 = no timer reads
   int l2_evict_first = 1;      // the SpMV's operator stream is fetched with the evict_first L2 priority (solver.cu bulk_g2s_hint)
-  int vec_reverse = 1;         // BiCGStab s- and x/r-updates walk their vectors back to front (L2 reuse of the SpMV's output tail)
+  int vec_reverse = 1;         // BiCGStab s-update (elementwise, no reduction) walks its vectors back to front (L2 reuse of the SpMV's output tail)
   int trace = 0;               // print the device time of every operation of BiCGStab iteration 4
 };
 

@@ -254,3 +254,124 @@ def test_cpp_driver_matches_python_mirror_and_oracle(tmp_path):
     assert np.allclose(table[-1, 1:7:2], cA, rtol=1e-6)
     assert np.allclose(table[-1, 8::2], vT, rtol=1e-6, atol=1e-12)
     gpu.close()
+
+
+def _write_gmsh_with_faces(path, conn, xyz, ids, faces):
+    """Gmsh 2.2 with tagged boundary faces (type 2 triangle / 3 quadrangle) in front of the volume elements, like a mesh
+    written by Gmsh with physical surfaces: `faces` = [(tag, node ids)]."""
+    vtype = 4 if conn.shape[1] == 4 else 5
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % xyz.shape[0])
+        for k, (x, y, z) in enumerate(xyz):
+            f.write("%d %.17g %.17g %.17g\n" % (k + 1, x, y, z))
+        f.write("$EndNodes\n$Elements\n%d\n" % (conn.shape[0] + len(faces)))
+        k = 1
+        for tag, nodes in faces:
+            f.write("%d %d 2 %d %d %s\n" % (k, 2 if len(nodes) == 3 else 3, tag, tag, " ".join(str(v + 1) for v in nodes)))
+            k += 1
+        for e, c in enumerate(conn):
+            f.write("%d %d 2 %d %d %s\n" % (k, vtype, ids[e], ids[e], " ".join(str(v + 1) for v in c)))
+            k += 1
+        f.write("$EndElements\n")
+
+
+def _tagged_faces(case):
+    from oracle import solid as S
+    out = []
+    for e, s, b in zip(case.side_elem, case.side_no, case.side_bc):
+        out.append((case.bc_ids[b], [int(case.conn[e, l]) for l in S.SIDE_NODES[case.elem_type][s]]))
+    return out
+
+
+_TIGHT = ("solver/nonlinear/max_nonlinear_iterations = 25\nsolver/nonlinear/relative_step_tolerance = 1e-11\n"
+          "solver/nonlinear/relative_residual_tolerance = 1e-13\nsolver/nonlinear/absolute_residual_tolerance = 1e-9\n"
+          "solver/linear/initial_linear_tolerance = 1e-10\n")
+
+
+@pytest.mark.parametrize("et", [cases.TET4, cases.HEX8])
+def test_cpp_driver_solid(tmp_path, et):
+    """rdc_driver -m solid = the loop of solid.C:81-108 over the C ABI: mesh with tagged boundary faces, input.dat in the
+    layout of run/Solid/uniaxial_compression, final positions and element stresses against the oracle's load steps."""
+    import solid_cases as SC
+    from oracle import solid as S
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
+    c = SC.compression_case(et, n=3, penalty=1.0e6)
+    d = str(tmp_path)
+    _write_gmsh_with_faces(os.path.join(d, "cube.msh"), c.conn, c.xund, np.zeros(c.E, dtype=int), _tagged_faces(c))
+    with open(os.path.join(d, "input.dat"), "w") as f:
+        f.write("input_GMSH = cube.msh\nloading_step = 0.25\noutput_PARAVIEW = out\n" + _TIGHT)
+        f.write("BCs = ' 0 5 '\nBC/0/displacement/0 = +0.000\nBC/0/displacement/1 = +0.000\nBC/0/displacement/2 = +0.000\n")
+        f.write("BC/5/displacement/0 = NAN\nBC/5/displacement/1 = NAN\nBC/5/displacement/2 = -0.750\nBCs/displacement_penalty = 1.e+6\n")
+        f.write("materials = ' 0 '\nmaterial/0/Neohookean/Young = 1.0e+4\n")     # misspelt like the shipped file: defaults apply
+    sol = os.path.join(d, "x.bin")
+    out = subprocess.run([os.path.join(ROOT, "driver", "rdc_driver"), "-m", "solid", os.path.join(d, "input.dat"), "ksp=0",
+                          "vtu=binary", "solution_out=" + sol], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    raw = np.fromfile(sol)
+    x_drv, p_drv, vm_drv = raw[:3 * c.N], raw[3 * c.N:3 * c.N + c.E], raw[3 * c.N + c.E:]
+    c.opts.update(max_nonlinear_iterations=25, relative_step_tolerance=1e-11, relative_residual_tolerance=1e-13,
+                  absolute_residual_tolerance=1e-9, initial_linear_tolerance=1e-10)
+    orc = S.OracleSolid(c)
+    x = c.xund.copy().ravel()
+    for l in range(1, 5):
+        x, info = orc.newton(x, 0.25 * l)
+        assert info["converged"]
+    assert np.linalg.norm(x_drv - x) <= 1e-8 * np.linalg.norm(x)
+    po, vo, _ = orc.post(x, 1.0)
+    scale = np.abs(po).max() + vo.max()
+    assert np.abs(p_drv - po).max() <= 1e-6 * scale and np.abs(vm_drv - vo).max() <= 1e-6 * scale
+    arrays = _read_appended_vtu(os.path.join(d, "out-4.vtu"))      # solid.C:27-44 variable names, the mesh at its moved position
+    assert np.allclose(arrays["u_z"], x_drv.reshape(-1, 3)[:, 2] - c.xund[:, 2], atol=1e-12)
+    assert np.allclose(arrays["position"].reshape(-1, 3), x_drv.reshape(-1, 3), atol=1e-12)
+
+
+def test_cpp_driver_coupled_hcc_with_solid(tmp_path):
+    """coupled_hcc.C:93-140 with the solid solves switched on: the mesh moves at the loading time points and the
+    reaction-diffusion system is assembled on the moved mesh afterwards (rdc_update_coords).  Checked against the same
+    sequence driven from Python: oracle Newton for the mesh positions, oracle RD steps on those positions."""
+    import solid_cases as SC
+    from oracle import solid as S
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
+    sc = SC.growth_case(cases.TET4, n=3)
+    conn, xyz = sc.conn, sc.xund
+    p, u0, ef, nf = cases.case(cases.HCC, conn, xyz, "full")
+    d = str(tmp_path)
+    _write_gmsh_with_faces(os.path.join(d, "m.msh"), conn, xyz, 3000 + sc.mat_of, _tagged_faces(sc))
+    np.savetxt(os.path.join(d, "nodal.dat"), np.asarray(u0).reshape(-1, 3), fmt="%.17g")
+    nsteps, dt, nload = 4, cases.DT[cases.HCC], 2
+    extra = f"input_GMSH = m.msh\ninput_nodal = nodal.dat\ntime_step = {dt}\nnumber_of_time_steps = {nsteps}\nnumber_of_loading_steps = {nload}\n" + _TIGHT
+    extra += "BCs = ' 2000 2002 '\nBC/2000/displacement/0 = 0\nBC/2000/displacement/1 = 0\nBC/2000/displacement/2 = 0\n"
+    extra += "BC/2002/displacement/0 = NAN\nBC/2002/displacement/1 = NAN\nBC/2002/displacement/2 = 0\nBCs/displacement_penalty = 1.e+8\n"
+    extra += "materials = ' 3000 3001 '\n"
+    for m, row in zip((3000, 3001), sc.mats):
+        for key, v in zip(("Young", "Poisson", "FibreStiffness", "VolumetricStretchRatio/rate_0", "VolumetricStretchRatio/rate_1",
+                           "VolumetricStretchRatio/rate_2"), row):
+            extra += f"material/{m}/Hyperelastic/{key} = {float(v)!r}\n"
+    _write_input(os.path.join(d, "input.dat"), cases.HCC, p, extra)
+    sol = os.path.join(d, "u.bin")
+    out = subprocess.run([os.path.join(ROOT, "driver", "rdc_driver"), "-m", "coupled_hcc", os.path.join(d, "input.dat"), "ksp=0",
+                          "solution_out=" + sol], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("Newton iterations") == nload
+    u_drv = np.fromfile(sol)
+    # the same sequence with the oracles
+    sc.opts.update(max_nonlinear_iterations=25, relative_step_tolerance=1e-11, relative_residual_tolerance=1e-13,
+                   absolute_residual_tolerance=1e-9, initial_linear_tolerance=1e-10)
+    so = S.OracleSolid(sc)
+    x = xyz.copy().ravel()
+    orc = cases.oracle_problem(cases.HCC, cases.TET4, conn, xyz, p, u0, ef, nf)
+    pseudo, loading_step = 0.0, dt * nsteps / nload
+    for t in range(1, nsteps + 1):
+        if t % (nsteps // nload) == 0:
+            pseudo += loading_step
+        orc.step(dt, pc=O.PC_ILU)
+        if t % (nsteps // nload) == 0:
+            x, info = so.newton(x, pseudo)
+            assert info["converged"]
+            orc.xyz = np.ascontiguousarray(x.reshape(-1, 3))
+    assert np.linalg.norm(u_drv - orc.u) <= 1e-7 * np.linalg.norm(orc.u)
+    # and the mesh really moved: the run on the fixed mesh differs
+    out2 = subprocess.run([os.path.join(ROOT, "driver", "rdc_driver"), "-m", "coupled_hcc", os.path.join(d, "input.dat"), "ksp=0", "solid=off",
+                           "solution_out=" + sol], capture_output=True, text=True, timeout=300)
+    assert out2.returncode == 0, out2.stdout + out2.stderr
+    assert np.linalg.norm(np.fromfile(sol) - u_drv) > 1e-6 * np.linalg.norm(u_drv)
