@@ -333,6 +333,7 @@ def test_cpp_driver_coupled_hcc_with_solid(tmp_path):
     from oracle import solid as S
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
     sc = SC.growth_case(cases.TET4, n=3)
+    sc.mats[1, 3:] = 4.0      # strong growth: the moved mesh changes the RD solution by 9e-8, well above the 1e-9 parity bar
     conn, xyz = sc.conn, sc.xund
     p, u0, ef, nf = cases.case(cases.HCC, conn, xyz, "full")
     d = str(tmp_path)
@@ -369,9 +370,9 @@ def test_cpp_driver_coupled_hcc_with_solid(tmp_path):
             x, info = so.newton(x, pseudo)
             assert info["converged"]
             orc.xyz = np.ascontiguousarray(x.reshape(-1, 3))
-    assert np.linalg.norm(u_drv - orc.u) <= 1e-7 * np.linalg.norm(orc.u)
+    assert np.linalg.norm(u_drv - orc.u) <= 1e-9 * np.linalg.norm(orc.u)
     # and the mesh really moved: the run on the fixed mesh differs
     out2 = subprocess.run([os.path.join(ROOT, "driver", "rdc_driver"), "-m", "coupled_hcc", os.path.join(d, "input.dat"), "ksp=0", "solid=off",
                            "solution_out=" + sol], capture_output=True, text=True, timeout=300)
     assert out2.returncode == 0, out2.stdout + out2.stderr
-    assert np.linalg.norm(np.fromfile(sol) - u_drv) > 1e-6 * np.linalg.norm(u_drv)
+    assert np.linalg.norm(np.fromfile(sol) - u_drv) > 3e-8 * np.linalg.norm(u_drv)
