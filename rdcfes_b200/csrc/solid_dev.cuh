@@ -125,11 +125,14 @@ RDC_HD void solid_point(const double (*Xu)[3], const double (*dphi)[3], const do
 template <int NEN>
 RDC_HD void solid_row(const FeTable& T, const double (*Xc)[3], const double (*Xu)[3], const double* mat, double pseudo_time,
                       const double* eta, int li, double* R, double* K, int kstride) {
-  constexpr int NQP = NEN == 4 ? 5 : 8;
+  // TET4: the map is affine, so grad phi, F and with them sigma and the tangent are the same at all five points of the
+  // rule -- one evaluation carries the whole weight sum(w_q) = 1/6 (w_0 = -2/15 times -5/4).  HEX8: per point.
+  constexpr int NQP = NEN == 4 ? 1 : 8;
 #pragma unroll 1
   for (int q = 0; q < NQP; q++) {
     double dphi[NEN][3], JxW;
     solid_geometry<NEN>(T, q, Xc, dphi, JxW);
+    if (NEN == 4) JxW *= -1.25;
     SolidPoint S;
     solid_point<NEN>(Xu, dphi, mat, pseudo_time, eta, S);
     double g[3] = {dphi[0][0], dphi[0][1], dphi[0][2]};
@@ -229,7 +232,7 @@ RDC_HD void solid_bc_row(const double (*Xc)[3], const double (*Xu)[3], const dou
 template <int NEN>
 RDC_HD void solid_post_elem(const FeTable& T, const double (*Xc)[3], const double (*Xu)[3], const double* mat, double pseudo_time,
                             const double* eta, double* out /* {p, vm, f0, f1, f2} */) {
-  constexpr int NQP = NEN == 4 ? 5 : 8;
+  constexpr int NQP = NEN == 4 ? 1 : 8;   // TET4: constant stress, the mean over the rule's points is the value itself
   double s00 = 0, s11 = 0, s22 = 0, s01 = 0, s12 = 0, s02 = 0, f[3] = {0, 0, 0};
 #pragma unroll 1
   for (int q = 0; q < NQP; q++) {
