@@ -13,13 +13,17 @@
 //   *older = *old; *old = *cur  -> RdcAdapter::rotate()          (adpm.C:71-72, ...)
 //   check_solution(es)          -> RdcAdapter::check_solution()  (adpm.C:654-688, ...)
 //   save_solution / paraview    -> RdcAdapter::pull_solution()   (adpm.C:79-83: output steps only)
+//   SolidSystem::save_initial_mesh / run_solver / post_process -> RdcSolidAdapter (solid_system.C:26-48, 373-538), see below
 //
 // The parameter vector is read from es.parameters with the very keys input() stored (adpm.C:130-226 ...), through the
 // table shared with the stand-alone driver (driver/param_tables.h); the angles are already in radians there
 // (adpm.C:192,212) and RIPF's fraction counts are ints (ripf.C:228-231).
 #pragma once
+#include <algorithm>
 #include <memory>
 #include <optional>
+#include <set>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -200,6 +204,158 @@ class RdcLinearSolver : public libMesh::LinearSolver<libMesh::Number> {
   RdcAdapter& a_;
   int ksp_;
   libMesh::LinearConvergenceReason reason_ = libMesh::CONVERGED_ITERATING;
+};
+
+// ---- SolidSystem (solid_system.C): the Newton solve and the post-processing behind rdc_solid_* -------------------------
+// Used from the three members the drivers call (solid.C:68,96-99, coupled_hcc.C:76,117-128):
+//   SolidSystem::save_initial_mesh() -> RdcSolidAdapter::hand_over()     after the reference's own copy into the auxiliary system
+//   SolidSystem::run_solver()        -> RdcSolidAdapter::run_solver()    instead of this->solve() (NewtonSolver)
+//   SolidSystem::post_process()      -> RdcSolidAdapter::post_process()  instead of the element loop (solid_system.C:422-531)
+// `sys` is the SolidSystem ("x","y","z" = current node positions), es holds "SolidSystem::auxiliary" (undeformed positions),
+// "SolidSystem::fibre", "SolidSystem::pressure", "SolidSystem::von_mises" and the parameters of solid.C:input().
+class RdcSolidAdapter {
+ public:
+  RdcSolidAdapter(libMesh::EquationSystems& es, libMesh::System& sys) : es_(es), sys_(sys) {}
+  ~RdcSolidAdapter() { rdc_destroy(ctx_); }
+  rdc_ctx* ctx() { return ctx_; }
+
+  void hand_over() {
+    using namespace libMesh;
+    const MeshBase& mesh = es_.get_mesh();
+    const System& aux = es_.get_system("SolidSystem::auxiliary");
+    const System& fib = es_.get_system("SolidSystem::fibre");
+    const int nen = (*mesh.active_elements_begin())->n_nodes();
+    const dof_id_type N = mesh.n_nodes();
+    std::vector<int32_t> conn, base(N);
+    std::vector<int> sub;
+    for (const auto& elem : mesh.active_element_ptr_range()) {
+      for (unsigned l = 0; l < elem->n_nodes(); l++) conn.push_back(elem->node_id(l));
+      sub.push_back(elem->subdomain_id());
+    }
+    const size_t E = sub.size();
+    std::vector<double> xund(3 * (size_t)N);
+    for (const auto& node : mesh.node_ptr_range()) {
+      base[node->id()] = (int32_t)node->dof_number(sys_.number(), 0, 0);     // x, y, z are contiguous at a node
+      for (unsigned d = 0; d < 3; d++) xund[3 * (size_t)node->id() + d] = aux.current_solution(node->dof_number(aux.number(), d, 0));
+    }
+    check(rdc_create(&ctx_, RDC_SOLID, nen, N, (int64_t)E, conn.data(), xund.data(), base.data(), -1), "rdc_create");
+    check(rdc_solid_set_reference(ctx_, xund.data()), "rdc_solid_set_reference");
+    push_positions();
+    // materials: one row per distinct subdomain id, keys of solid.C:276-291 (read per element at solid_system.C:182-189)
+    std::vector<int> ids(sub);
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    std::vector<double> mats;
+    for (int id : ids) {
+      const std::string k = "material/" + std::to_string(id) + "/Hyperelastic/";
+      for (const char* key : {"Young", "Poisson", "FibreStiffness", "VolumetricStretchRatio/rate_0", "VolumetricStretchRatio/rate_1",
+                              "VolumetricStretchRatio/rate_2"})
+        mats.push_back(es_.parameters.get<Real>(k + key));
+    }
+    std::vector<int32_t> mat_of(E);
+    for (size_t e = 0; e < E; e++) mat_of[e] = (int32_t)(std::lower_bound(ids.begin(), ids.end(), sub[e]) - ids.begin());
+    check(rdc_solid_set_materials(ctx_, (int)ids.size(), mats.data(), mat_of.data()), "rdc_solid_set_materials");
+    // reference fibre direction: variables 0-2 of "SolidSystem::fibre" (solid_system.C:205-213)
+    std::vector<double> fibres(3 * E);
+    std::vector<dof_id_type> di;
+    size_t e = 0;
+    for (const auto& elem : mesh.active_element_ptr_range()) {
+      for (unsigned d = 0; d < 3; d++) {
+        fib.get_dof_map().dof_indices(elem, di, d);
+        fibres[3 * e + d] = (*fib.current_local_solution)(di[0]);
+      }
+      e++;
+    }
+    check(rdc_solid_set_fibres(ctx_, fibres.data()), "rdc_solid_set_fibres");
+    // boundary conditions: "BCs" ids, their displacement Points, every (elem, side) that carries one (solid_system.C:288-304)
+    std::vector<int> bc_ids;
+    {
+      std::stringstream ss(es_.parameters.get<std::string>("BCs"));
+      std::string tok;
+      std::set<int> uniq;
+      while (ss >> tok) { int n; if (std::stringstream(tok) >> n) uniq.insert(n); }   // export_integers (utils.h:268-287)
+      bc_ids.assign(uniq.begin(), uniq.end());
+    }
+    std::vector<double> disp;
+    for (int id : bc_ids) {
+      const Point p = es_.parameters.get<Point>("BC/" + std::to_string(id) + "/displacement");
+      for (unsigned d = 0; d < 3; d++) disp.push_back(p(d));
+    }
+    std::vector<int64_t> side_elem;
+    std::vector<int32_t> side_no, side_bc;
+    e = 0;
+    for (const auto& elem : mesh.active_element_ptr_range()) {
+      for (auto s : elem->side_index_range())
+        for (size_t b = 0; b < bc_ids.size(); b++)
+          if (mesh.get_boundary_info().has_boundary_id(elem, s, (boundary_id_type)bc_ids[b])) {
+            side_elem.push_back((int64_t)e); side_no.push_back((int32_t)s); side_bc.push_back((int32_t)b);
+          }
+      e++;
+    }
+    check(rdc_solid_set_bcs(ctx_, (int)bc_ids.size(), disp.data(), (int64_t)side_elem.size(), side_elem.data(), side_no.data(), side_bc.data(),
+                            es_.parameters.get<Real>("BCs/displacement_penalty")), "rdc_solid_set_bcs");
+  }
+
+  // current positions: libMesh solution vector -> device (after anything on the host changed them)
+  void push_positions() {
+    std::vector<double> x(sys_.solution->size());
+    for (libMesh::dof_id_type i = 0; i < sys_.solution->size(); i++) x[i] = (*sys_.solution)(i);
+    check(rdc_set_solution(ctx_, x.data()), "rdc_set_solution");
+  }
+  // device -> libMesh solution vector, then the mesh follows (SolidSystem::update -> mesh_position_set, solid_system.C:101-108)
+  void pull_positions() {
+    std::vector<double> x((size_t)rdc_n_dofs(ctx_));
+    check(rdc_get_solution(ctx_, x.data()), "rdc_get_solution");
+    for (libMesh::dof_id_type i = sys_.solution->first_local_index(); i < sys_.solution->last_local_index(); i++) sys_.solution->set(i, x[i]);
+    sys_.solution->close();
+    sys_.update();
+  }
+
+  // SolidSystem::run_solver (solid_system.C:373-392): the Newton solve with the options solid_system.C:80-98 gives NewtonSolver
+  bool run_solver(int ksp = RDC_KSP_GMRES) {
+    using libMesh::Real;
+    const double opts[7] = {(double)es_.parameters.get<int>("solver/nonlinear/max_nonlinear_iterations"),
+                            es_.parameters.get<Real>("solver/nonlinear/relative_step_tolerance"),
+                            es_.parameters.get<Real>("solver/nonlinear/relative_residual_tolerance"),
+                            es_.parameters.get<Real>("solver/nonlinear/absolute_residual_tolerance"),
+                            es_.parameters.get<bool>("solver/nonlinear/require_reduction") ? 1.0 : 0.0,
+                            (double)es_.parameters.get<int>("solver/linear/max_linear_iterations"),
+                            es_.parameters.get<Real>("solver/linear/initial_linear_tolerance")};
+    check(rdc_solid_newton(ctx_, es_.parameters.get<Real>("pseudo_time"), opts, ksp, info_), "rdc_solid_newton");
+    pull_positions();
+    return info_[3] != 0.0;
+  }
+  const double* last_info() const { return info_; }   // {newton iterations, linear iterations, residual, converged}
+
+  // SolidSystem::post_process (solid_system.C:394-538): fills "SolidSystem::pressure", "::von_mises" and variables 3-5 of "::fibre"
+  void post_process() {
+    using namespace libMesh;
+    const MeshBase& mesh = es_.get_mesh();
+    System& ps = es_.get_system("SolidSystem::pressure");
+    System& vs = es_.get_system("SolidSystem::von_mises");
+    System& fs = es_.get_system("SolidSystem::fibre");
+    const size_t E = mesh.n_elem();
+    std::vector<double> p(E), vm(E), f(3 * E);
+    check(rdc_solid_post_process(ctx_, es_.parameters.get<Real>("pseudo_time"), p.data(), vm.data(), f.data()), "rdc_solid_post_process");
+    std::vector<dof_id_type> di;
+    size_t e = 0;
+    for (const auto& elem : mesh.active_element_ptr_range()) {
+      ps.get_dof_map().dof_indices(elem, di); ps.solution->set(di[0], p[e]);
+      vs.get_dof_map().dof_indices(elem, di); vs.solution->set(di[0], vm[e]);
+      for (unsigned d = 0; d < 3; d++) { fs.get_dof_map().dof_indices(elem, di, d + 3); fs.solution->set(di[0], f[3 * e + d]); }
+      e++;
+    }
+    ps.solution->close(); vs.solution->close(); fs.solution->close();
+  }
+
+ private:
+  void check(int rc, const char* what) {
+    if (rc) libmesh_error_msg(std::string(what) + ": " + rdc_last_error(ctx_));
+  }
+  libMesh::EquationSystems& es_;
+  libMesh::System& sys_;
+  rdc_ctx* ctx_ = nullptr;
+  double info_[4] = {0, 0, 0, 0};
 };
 
 }  // namespace rdcfes

@@ -74,3 +74,95 @@ def test_adapter_runs_the_patched_time_loop(model, ksp, tmp_path):
     # solvers may take different branches there from the second step on
     tol = 1e-6 if model == cases.RIPF else 1e-8
     assert np.linalg.norm(u - orc.u) <= tol * np.linalg.norm(orc.u)
+
+
+# ---- the SolidSystem glue (RdcSolidAdapter) next to the reference's own solid_system.C ------------------------------------
+SOLID_EXE = os.path.join(HERE, "adapter", "solid_adapter_check")
+REF_SOLID = "/root/reference/src/solid_system.C"
+
+
+def build_solid_adapter_check():
+    """One program with both sides: the reference's solid_system.C + eig3.C compiled unchanged against the libMesh stand-in,
+    and the device path reached through adapter/rdc_libmesh_adapter.h.  Needs the reference sources; the binary travels."""
+    so = B.build()
+    src = os.path.join(HERE, "adapter", "solid_adapter_check.cpp")
+    if not os.path.exists(REF_SOLID):
+        return SOLID_EXE if os.path.exists(SOLID_EXE) else None
+    deps = [src, os.path.join(ROOT, "adapter", "rdc_libmesh_adapter.h"), os.path.join(ROOT, "oracle", "ref_shim", "libmesh", "shim.h"),
+            os.path.join(ROOT, "oracle", "ref_shim", "ref_solid.cpp"), so]
+    if os.path.exists(SOLID_EXE) and all(os.path.getmtime(SOLID_EXE) >= os.path.getmtime(d) for d in deps):
+        return SOLID_EXE
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-w", "-ffp-contract=off", "-I", os.path.join(ROOT, "oracle", "ref_shim"),
+                           f'-DREF_SOURCE="{REF_SOLID}"', "-o", SOLID_EXE, src, "/root/reference/src/eig3.C",
+                           "-L", os.path.dirname(so), "-lrdcgpu", "-Wl,-rpath," + os.path.dirname(so)])
+    return SOLID_EXE
+
+
+def test_solid_adapter_compiles_against_the_libmesh_interface():
+    exe = build_solid_adapter_check()
+    if exe is None:
+        pytest.skip("reference sources not on this machine and no prebuilt binary")
+    assert os.path.exists(exe)
+
+
+def _write_solid_case(path, c, xpert, pseudo_time, nload, loading_step):
+    se, sn, sb, bd = c.arrays()
+    with open(path, "w") as f:
+        f.write(f"{c.elem_type} {c.N} {c.E}\n")
+        for arr in (c.xund, xpert, c.conn, c.mat_of if c.mat_of is not None else np.zeros(c.E, dtype=np.int32)):
+            a = np.asarray(arr).reshape(1, -1)
+            np.savetxt(f, a, fmt="%d" if a.dtype.kind == "i" else "%.17g")
+        f.write(f"{c.mats.shape[0]}\n")
+        np.savetxt(f, c.mats.reshape(1, -1), fmt="%.17g")
+        np.savetxt(f, (c.fibres if c.fibres is not None else np.ones((c.E, 3))).reshape(1, -1), fmt="%.17g")
+        f.write(f"{len(c.bc_ids)}\n")
+        for i, d in zip(c.bc_ids, c.bc_disp):
+            f.write(f"{i} " + " ".join("nan" if v != v else repr(float(v)) for v in d) + "\n")
+        f.write(f"{se.shape[0]}\n")
+        for k in range(se.shape[0]):
+            f.write(f"{se[k]} {sn[k]} {sb[k]}\n")
+        f.write(f"{c.penalty!r} {pseudo_time!r} {nload} {loading_step!r}\n")
+        f.write(" ".join(repr(float(v)) for v in c.opts_vector()) + "\n")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("et", [cases.TET4, cases.HEX8])
+def test_solid_adapter_against_the_reference_solid_system(et, tmp_path):
+    """Device Jacobian / residual / post-processing, reached from libMesh objects through RdcSolidAdapter, against the
+    reference's own element_time_derivative + side_time_derivative + post_process in the same process; then load steps through
+    RdcSolidAdapter::run_solver against the oracle's Newton driver."""
+    import solid_cases as SC
+    from oracle import solid as S
+    exe = build_solid_adapter_check()
+    if exe is None:
+        pytest.skip("no solid_adapter_check binary")
+    # (A), (B): every term switched on
+    c = SC.general_case(et, n=3)
+    inp, out = tmp_path / "case.txt", tmp_path / "out.txt"
+    _write_solid_case(inp, c, SC.perturbed(c, amp=0.01), 0.3, 0, 0.1)
+    res = subprocess.run([exe, str(inp), str(out)], capture_output=True, text=True, timeout=300)
+    print(res.stdout, res.stderr[-2000:])
+    assert res.returncode == 0
+    head = np.loadtxt(out, max_rows=1)
+    assert head[0] == 1, "sparsity pattern differs from the one the reference touches"
+    assert head[1] <= 1e-12 and head[2] <= 1e-12, head          # Jacobian, residual
+    assert head[3] <= 1e-10 and head[4] <= 1e-12, head          # stresses, fibre vector
+    # (C): load steps of the compression problem, tight tolerances
+    c = SC.compression_case(et, n=3, penalty=1.0e6)
+    c.opts.update(max_nonlinear_iterations=25, relative_step_tolerance=1e-11, relative_residual_tolerance=1e-13,
+                  absolute_residual_tolerance=1e-9, initial_linear_tolerance=1e-10)
+    c.mat_of = np.zeros(c.E, dtype=np.int32)
+    _write_solid_case(inp, c, c.xund, 0.0, 3, 0.1)
+    res = subprocess.run([exe, str(inp), str(out)], capture_output=True, text=True, timeout=300)
+    print(res.stdout, res.stderr[-2000:])
+    assert res.returncode == 0
+    head = np.loadtxt(out, max_rows=1)
+    assert head[5] == 1
+    x = np.loadtxt(out, skiprows=1)
+    orc = S.OracleSolid(c)
+    xo = c.xund.copy().ravel()
+    for l in (1, 2, 3):
+        xo, info = orc.newton(xo, 0.1 * l)
+        assert info["converged"]
+    assert np.linalg.norm(x - xo) <= 1e-8 * np.linalg.norm(xo)
