@@ -297,6 +297,37 @@ def measure(args, n, world, rank, local, steps, warmup, ksp, with_e2e=True, samp
     return res
 
 
+def solid_secondary(n=60):
+    """SURVEY 8(f) rank 3 next to the headline: the solid-mechanics path (solid_system.C) on a 1.3 M-tet cube --
+    uniaxial compression like run/Solid/uniaxial_compression (bottom clamped, top pushed down, penalty 1e8, the shipped
+    Newton tolerances), two load steps from the undeformed state.  Device path only (rdcfes_b200/solid.py over the C ABI);
+    wall-clock around calls that synchronise; parity of this path is the business of tests/test_gpu_solid.py."""
+    from rdcfes_b200 import solid as G
+    conn, xyz = synth.kuhn_cube(n, 1.5)
+    g = G.SolidSystem(4, conn, xyz)
+    e0, s0 = synth.boundary_sides(conn, xyz, 2, 0.0)
+    e1, s1 = synth.boundary_sides(conn, xyz, 2, xyz[:, 2].max())
+    g.set_bcs([[0.0, 0.0, 0.0], [float("nan"), float("nan"), -0.75]], np.concatenate([e0, e1]), np.concatenate([s0, s1]),
+              np.concatenate([np.zeros(e0.size, dtype=np.int32), np.ones(e1.size, dtype=np.int32)]), 1.0e8)
+    g.options.update(max_nonlinear_iterations=10)
+    g.ksp = G.KSP_BICGSTAB
+    g.assemble(0.1)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        g.assemble(0.1)
+    asm_ms = (time.perf_counter() - t0) / 10 * 1e3
+    steps = []
+    for l in (1, 2):
+        t0 = time.perf_counter()
+        info = g.run_solver(0.1 * l)
+        steps.append({"ms": (time.perf_counter() - t0) * 1e3, **info})
+    z = g.get_positions()[:, 2]
+    g.close()
+    return {"what": "SolidSystem load steps (neo-Hookean, penalty BCs), k_solid_assemble + k_solid_bc + BiCGStab/Jacobi Newton systems",
+            "workload": f"unit-cube Kuhn tets n={n} ({conn.shape[0]} tets, {xyz.shape[0]} nodes), pseudo-time 0.1 and 0.2",
+            "assemble_ms": asm_ms, "load_steps": steps, "top_face_z": float(z.max())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,6 +341,7 @@ def main():
     ap.add_argument("--ksp", type=int, default=2, help="0 GMRES(30) (libMesh default), 1 CG, 2 BiCGStab; all Jacobi, rtol 1e-12")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling measurement (N x 10.1 M tets)")
+    ap.add_argument("--no-solid", action="store_true", help="N = 1: skip the secondary solid-mechanics measurement (SURVEY 8(f) rank 3)")
     ap.add_argument("--partitioner", type=int, default=0)
     ap.add_argument("--model", default="adpm", choices=["adpm", "pihna"],
                     help="adpm = the BASELINE.json workload; pihna = secondary 5-species measurement (no CPU baseline)")
@@ -457,6 +489,11 @@ def main():
         out["ksp_gmres30"] = gm
     if world > 1:
         dist.destroy_process_group()
+    if world == 1 and not args.no_solid and args.model == "adpm" and args.n >= 60:
+        try:
+            out["solid_mechanics"] = solid_secondary()
+        except Exception as exc:  # noqa: BLE001 -- a secondary number must not take the headline line down
+            out["solid_mechanics"] = {"error": str(exc)[:300]}
     if want_cpu:  # reported at N = 1 only
         ncores = os.cpu_count() or 1
         state = {}

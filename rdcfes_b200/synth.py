@@ -269,3 +269,21 @@ def hcc_fields(xyz):
     u[:, 1] = 0.4 * _blob(xyz, c, 0.2 * L.max())
     u[:, 2] = 0.15 * _blob(xyz, c, 0.1 * L.max())
     return u
+
+
+# [upstream] Tet4/Hex8::side_nodes_map: local nodes of side s in libMesh's side numbering
+SIDE_NODES = {4: ((0, 2, 1), (0, 1, 3), (1, 2, 3), (2, 0, 3)),
+              8: ((0, 3, 2, 1), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7), (4, 5, 6, 7))}
+
+
+def boundary_sides(conn, xyz, axis, value, tol=1e-9):
+    """(elem, side) of the element sides that lie in the plane x[axis] = value (what a tagged physical surface of a Gmsh file
+    becomes in libMesh's BoundaryInfo): the boundary-condition sides of the solid-mechanics cases."""
+    conn = np.asarray(conn)
+    on = np.abs(np.asarray(xyz)[:, axis] - value) < tol
+    elems, sides = [], []
+    for s, loc in enumerate(SIDE_NODES[conn.shape[1]]):
+        hit = np.nonzero(on[conn[:, list(loc)]].all(axis=1))[0]
+        elems.append(hit)
+        sides.append(np.full(hit.shape, s, dtype=np.int32))
+    return np.concatenate(elems).astype(np.int64), np.concatenate(sides)
