@@ -303,6 +303,7 @@ def solid_secondary(n=60):
     Newton tolerances), two load steps from the undeformed state.  Device path only (rdcfes_b200/solid.py over the C ABI);
     wall-clock around calls that synchronise; parity of this path is the business of tests/test_gpu_solid.py."""
     from rdcfes_b200 import solid as G
+    from rdcfes_b200 import synth
     conn, xyz = synth.kuhn_cube(n, 1.5)
     g = G.SolidSystem(4, conn, xyz)
     e0, s0 = synth.boundary_sides(conn, xyz, 2, 0.0)
