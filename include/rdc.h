@@ -227,8 +227,10 @@ int rdc_region_last_mean(rdc_ctx*, int var, double* mean /* [n_regions] */);
 
 /* ---- solid mechanics: SolidSystem of solid_system.C / solid.C / coupled_hcc.C:117-132 -----------
  * A context created with model RDC_SOLID holds the CURRENT node positions as its solution (rdc_set_solution /
- * rdc_get_solution, dof = 3*node + d unless node_dof_base says otherwise) -- solid.C:27-30, mesh_position_get/set.  One GPU
- * per context.  The Krylov solvers of rdc_solve (ksp) with point Jacobi solve the Newton systems.
+ * rdc_get_solution, dof = 3*node + d unless node_dof_base says otherwise) -- solid.C:27-30, mesh_position_get/set.  Works
+ * with rdc_create_distributed too (one process per GPU: owned rows, ghost positions and step vectors exchanged like the RDC
+ * systems', norms all-reduced in rank order so that every rank takes the same Newton decisions).  The Krylov solvers of
+ * rdc_solve (ksp) with point Jacobi solve the Newton systems.
  *   rdc_solid_set_reference  <- SolidSystem::save_initial_mesh (solid_system.C:26-48): undeformed positions [n_nodes*3]
  *   rdc_solid_set_materials  <- es.parameters "material/<id>/Hyperelastic/{Young,Poisson,FibreStiffness,
  *                               VolumetricStretchRatio/rate_0..2}" (solid.C:276-291, read at solid_system.C:182-189):

@@ -94,7 +94,6 @@ static int create_impl(rdc_ctx** out, int model, int elem_type, int64_t N, int64
     g_create_err = "rdc_create: cudaGetDevice failed";
     return RDC_E_NODEVICE;
   }
-  if (model == RDC_SOLID && nranks > 1) { g_create_err = "rdc_create_distributed: the solid path runs on one GPU per context"; return RDC_E_ARG; }
   rdc_ctx* c = new (std::nothrow) rdc_ctx();
   if (!c) return RDC_E_NOMEM;
   c->model = model; c->etype = elem_type; c->nen = elem_type == RDC_TET4 ? 4 : 8; c->nv = nv;

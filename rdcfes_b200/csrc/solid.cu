@@ -409,6 +409,8 @@ static int launch_solid_asm(rdc_ctx* c, const AsmArgs& A, const SolidArgs& S) {
 static int solid_assemble(rdc_ctx* c, SolidWork* W, double pseudo_time) {
   if (!W->d_xund) { c->err = "solid: rdc_solid_set_reference has not been called"; return RDC_E_STATE; }
   if (c->S.pairs_per_cta != 128) { c->err = "solid: the assembly kernel is built for 128 pairs per CTA"; return RDC_E_STATE; }
+  int grc = refresh_u_ghosts(c);   // distributed: the positions of the ghost nodes (rows of owned nodes see ghost-layer elements)
+  if (grc) return grc;
   AsmArgs A;
   A.conn = c->d_conn; A.xyz4 = c->d_xyz; A.u_old = c->d_u; A.efield = nullptr; A.aux0 = nullptr; A.aux1 = nullptr;
   A.n2e_ptr = c->d_n2e_ptr; A.pair = c->d_pair; A.rowptr = c->d_rowptr; A.cta_node = c->d_cta_node;
@@ -444,12 +446,15 @@ extern "C" int rdc_solid_assemble(rdc_ctx* c, double pseudo_time) {
   return RDC_OK;
 }
 
-// l2 norm of the first n entries of a device vector (deterministic)
+// l2 norm of the owned part (first n entries) of a device vector, over all ranks: deterministic, and bit-identical on every
+// rank (the ranks' sums are added in rank order), which the Newton driver's decisions rely on
 static int dev_norm(rdc_ctx* c, SolidWork* W, const double* v, size_t n, double* out) {
   const int nb = 296;
   k_sumsq_partial<<<nb, 256, 0, c->stream>>>(n, v, W->d_partial);
   k_sum_final<<<1, 256, 0, c->stream>>>(nb, W->d_partial, W->d_partial + 512);
   c->st.kernel_launches += 2;
+  int arc = allreduce_sum(c, W->d_partial + 512, 1);
+  if (arc) return arc;
   double s = 0.0;
   RDC_CUDA(cudaMemcpyAsync(&s, W->d_partial + 512, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
@@ -469,7 +474,6 @@ static int dev_norm(rdc_ctx* c, SolidWork* W, const double* v, size_t n, double*
 extern "C" int rdc_solid_newton(rdc_ctx* c, double pseudo_time, const double* opts, int ksp, double* info) {
   CHECK_SOLID(c);
   if (!opts) return RDC_E_ARG;
-  if (c->S.nranks > 1) { c->err = "the solid path runs on one GPU per context"; return RDC_E_STATE; }
   SolidWork* W;
   int rc = solid_work(c, &W);
   if (rc) return rc;
@@ -498,6 +502,7 @@ extern "C" int rdc_solid_newton(rdc_ctx* c, double pseudo_time, const double* op
           step *= 0.5;
           k_axpy<<<296, 256, 0, c->stream>>>(D, step, W->d_dx, c->d_u);
           c->st.kernel_launches++;
+          c->u_ghost_fresh = false;
           if ((rc = solid_assemble(c, W, pseudo_time))) return rc;
           if ((rc = dev_norm(c, W, c->d_rhs, D, &current_residual))) return rc;
         }
@@ -529,8 +534,9 @@ extern "C" int rdc_solid_newton(rdc_ctx* c, double pseudo_time, const double* op
     inner += its;
     linear_finished = its != max_lin;
     if ((rc = dev_norm(c, W, W->d_dx, D, &norm_delta))) return rc;
-    k_axpy<<<296, 256, 0, c->stream>>>(D, -1.0, W->d_dx, c->d_u);   // newton_iterate.add(-1, linear_solution)
+    k_axpy<<<296, 256, 0, c->stream>>>(D, -1.0, W->d_dx, c->d_u);   // newton_iterate.add(-1, linear_solution): owned dofs
     c->st.kernel_launches++;
+    c->u_ghost_fresh = false;                                       // the ghost copies follow at the next assembly
     RDC_CUDA(cudaGetLastError());
   }
   c->u_ghost_fresh = false;
@@ -549,6 +555,7 @@ extern "C" int rdc_solid_post_process(rdc_ctx* c, double pseudo_time, double* pr
   const HostSetup& S = c->S;
   const int64_t E = S.E_loc;
   if (!W->d_post) RDC_CUDA(cudaMalloc(&W->d_post, (size_t)std::max<int64_t>(E, 1) * 5 * sizeof(double)));
+  if ((rc = refresh_u_ghosts(c))) return rc;
   SolidArgs A;
   fill_solid_args(W, pseudo_time, &A);
   const int grid = (int)((E + 127) / 128);
@@ -559,11 +566,38 @@ extern "C" int rdc_solid_post_process(rdc_ctx* c, double pseudo_time, double* pr
   std::vector<double> h((size_t)E * 5);
   RDC_CUDA(cudaMemcpyAsync(h.data(), W->d_post, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   RDC_CUDA(cudaStreamSynchronize(c->stream));
-  for (int64_t le = 0; le < E; le++) {
-    const int64_t g = S.elem_glob[le];
-    if (press) press[g] = h[(size_t)le * 5];
-    if (vm) vm[g] = h[(size_t)le * 5 + 1];
-    if (fibre) for (int d = 0; d < 3; d++) fibre[(size_t)g * 3 + d] = h[(size_t)le * 5 + 2 + d];
+  std::vector<double> all;
+  const double* src = h.data();
+  std::vector<int64_t> glob_of;
+  if (S.nranks > 1) {
+    // every element is reported by exactly one rank -- the owner of its first node, on which it is always local -- and the
+    // ranks' pieces are summed (zeros elsewhere): every rank receives the full arrays, like es.reinit() leaves them in libMesh
+    std::vector<int32_t> first((size_t)E);
+    {
+      std::vector<int32_t> conn((size_t)E * c->nen);
+      RDC_CUDA(cudaMemcpy(conn.data(), c->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      for (int64_t le = 0; le < E; le++) first[le] = conn[(size_t)le * c->nen];
+    }
+    all.assign((size_t)S.E_glob * 5, 0.0);
+    for (int64_t le = 0; le < E; le++)
+      if (first[le] < S.n_owned)
+        for (int k = 0; k < 5; k++) all[(size_t)S.elem_glob[le] * 5 + k] = h[(size_t)le * 5 + k];
+    double* d_all = nullptr;
+    RDC_CUDA(cudaMalloc(&d_all, all.size() * sizeof(double)));
+    RDC_CUDA(cudaMemcpyAsync(d_all, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    rc = allreduce_sum(c, d_all, (int)all.size());
+    if (!rc && cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = RDC_E_CUDA;
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = RDC_E_CUDA;
+    cudaFree(d_all);
+    if (rc) { if (c->err.empty()) c->err = "solid post-processing: exchange failed"; return rc; }
+    src = all.data();
+  }
+  const int64_t n_out = S.nranks > 1 ? S.E_glob : E;
+  for (int64_t k = 0; k < n_out; k++) {
+    const int64_t g = S.nranks > 1 ? k : S.elem_glob[k];
+    if (press) press[g] = src[(size_t)k * 5];
+    if (vm) vm[g] = src[(size_t)k * 5 + 1];
+    if (fibre) for (int d = 0; d < 3; d++) fibre[(size_t)g * 3 + d] = src[(size_t)k * 5 + 2 + d];
   }
   return RDC_OK;
 }

@@ -25,13 +25,18 @@ def _ptr(a):
 
 
 class SolidSystem:
-    def __init__(self, elem_type, conn, xyz, device: int = -1):
+    def __init__(self, elem_type, conn, xyz, device: int = -1, rank: int = 0, nranks: int = 1, partitioner: int = 0, unique_id=None):
         self._L = _lib.load()
         self._h = C.c_void_p()
         self.conn = np.ascontiguousarray(conn, dtype=np.int32)
         xyz = np.ascontiguousarray(xyz, dtype=np.float64)
         self.n_nodes, self.n_elems = xyz.shape[0], self.conn.shape[0]
-        rc = self._L.rdc_create(C.byref(self._h), SOLID, elem_type, self.n_nodes, self.n_elems, _ptr(self.conn), _ptr(xyz), None, device)
+        if nranks > 1:   # one process per GPU, like the reference's MPI ranks; every rank passes the same replicated mesh
+            uid = C.create_string_buffer(unique_id, 128)
+            rc = self._L.rdc_create_distributed(C.byref(self._h), SOLID, elem_type, self.n_nodes, self.n_elems, _ptr(self.conn), _ptr(xyz),
+                                                None, device, rank, nranks, partitioner, C.cast(uid, C.c_void_p))
+        else:
+            rc = self._L.rdc_create(C.byref(self._h), SOLID, elem_type, self.n_nodes, self.n_elems, _ptr(self.conn), _ptr(xyz), None, device)
         if rc:
             raise _lib.RdcError(rc, self._L.rdc_last_error(None).decode())
         self.pseudo_time = 0.0
@@ -136,9 +141,9 @@ class SolidSystem:
         return st
 
 
-def from_case(case, device: int = -1) -> "SolidSystem":
+def from_case(case, device: int = -1, **dist) -> "SolidSystem":
     """Build a SolidSystem from an oracle.solid.SolidCase-like description (duck-typed: tests only)."""
-    s = SolidSystem(case.elem_type, case.conn, case.xund, device=device)
+    s = SolidSystem(case.elem_type, case.conn, case.xund, device=device, **dist)
     s.set_materials(case.mats, case.mat_of)
     s.set_fibres(case.fibres)
     se, sn, sb, bd = case.arrays()

@@ -131,6 +131,53 @@ def main():
             if not rel <= (1e-6 if model == cases.RIPF else 1e-8):
                 failures.append(f"{cases.NAMES[model]}: solution rel L2 {rel:.3e}")
         gpu.close()
+    # ---- solid mechanics, distributed: owned Jacobian rows, Newton load steps, post-processing ----------
+    import solid_cases as SC
+    from oracle import solid as S
+    from rdcfes_b200 import solid as G
+
+    def fresh_uid():
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(rs.make_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        return bytes(buf.cpu().numpy().tobytes())
+
+    c = SC.general_case(SC.TET4, n=n)
+    x = SC.perturbed(c, amp=0.03 / n)
+    g = G.from_case(c, device=local, rank=rank, nranks=world, partitioner=0, unique_id=fresh_uid())
+    g.set_positions(x)
+    g.assemble(0.3)
+    rows, rowptr, col, val, rhs = g.download_csr()
+    so = S.OracleSolid(c)
+    val_o, rhs_o = so.assemble(x, 0.3)
+    ref = np.concatenate([val_o[so.rowptr[r]:so.rowptr[r + 1]] for r in rows])
+    cols_ok = all(np.array_equal(col[rowptr[k]:rowptr[k + 1]], so.col[so.rowptr[r]:so.rowptr[r + 1]]) for k, r in enumerate(rows))
+    if not cols_ok or np.abs(val - ref).max() > 1e-12 * np.abs(val_o).max() or np.abs(rhs - rhs_o[rows]).max() > 1e-12 * np.abs(rhs_o).max():
+        failures.append(f"solid: Jacobian / residual rows differ on rank {rank}")
+    p, v, f = g.post_process(0.3)
+    po, vo, fo = so.post(x, 0.3)
+    if np.abs(p - po).max() > 1e-10 * (np.abs(po).max() + vo.max()) or np.abs(v - vo).max() > 1e-10 * (np.abs(po).max() + vo.max()) or \
+            np.abs(f - fo).max() > 1e-12:
+        failures.append(f"solid: post-processing differs on rank {rank}")
+    g.close()
+    c = SC.compression_case(SC.TET4, n=n, penalty=1.0e6)
+    c.opts.update(max_nonlinear_iterations=25, relative_step_tolerance=1e-11, relative_residual_tolerance=1e-13,
+                  absolute_residual_tolerance=1e-9, initial_linear_tolerance=1e-10)
+    for ksp in (G.KSP_GMRES, G.KSP_BICGSTAB):
+        g = G.from_case(c, device=local, rank=rank, nranks=world, partitioner=1 if ksp else 0, unique_id=fresh_uid())
+        g.ksp = ksp
+        so = S.OracleSolid(c)
+        xo = c.xund.copy().ravel()
+        for step in (1, 2):
+            info = g.run_solver(0.1 * step)
+            xg = g.get_positions().ravel()
+            if rank == 0:
+                xo, io = so.newton(xo, 0.1 * step)
+                rel = float(np.linalg.norm(xg - xo) / np.linalg.norm(xo))
+                print(f"solid x{world} ksp {ksp} load step {step}: {info}  rel L2 vs oracle {rel:.2e}", flush=True)
+                if not (info["converged"] and io["converged"] and rel <= 1e-8):
+                    failures.append(f"solid: load step {step} (ksp {ksp}): {info} {io} rel {rel:.3e}")
+        g.close()
     flag = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(flag)
     if failures:
