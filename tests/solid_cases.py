@@ -56,3 +56,55 @@ def growth_case(et, n=3):
     c.add_bc(2002, [np.nan, np.nan, 0.0], c.faces_where(lambda p: abs(p[2] - 1.0) < 1e-9))
     c.opts.update(max_nonlinear_iterations=30, relative_residual_tolerance=1e-6)
     return c
+
+
+# ---- the two solid cases the reference ships (run/Solid/*), from tests/golden/solid_*.npz --------------------------------
+def parse_input_dat(text):
+    """GetPot-style `key = value` lines ('#' comments, quotes stripped)."""
+    kv = {}
+    for ln in text.splitlines():
+        ln = ln.split("#")[0].strip()
+        if "=" in ln:
+            k, v = ln.split("=", 1)
+            kv[k.strip()] = v.strip().strip("'").strip()
+    return kv
+
+
+def shipped_case(name, tight=False):
+    """SolidCase of tests/golden/<name>.npz exactly as solid.C:input() reads the shipped input.dat: only the keys it asks for
+    count -- the files spell the material keys 'Neohookean' and the symmetry key 'solver/use_symmetry', which are never read,
+    so the defaults E = 1e3, nu = 0.3 (solid.C:279-283) and assembly_use_symmetry = false apply.  -> (case, kv, fixture)"""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    kv = parse_input_dat(str(d["input_dat"]))
+    conn, xyz = d["conn"], d["xyz"]
+    et = conn.shape[1]
+    mat_ids = sorted(int(v) for v in kv.get("materials", "0").split())
+    mats = []
+    for m in mat_ids:
+        k = f"material/{m}/Hyperelastic/"
+        mats.append([float(kv.get(k + "Young", 1.0e3)), float(kv.get(k + "Poisson", 0.3)), float(kv.get(k + "FibreStiffness", 0.0))] +
+                    [float(kv.get(k + f"VolumetricStretchRatio/rate_{r}", 0.0)) for r in range(3)])
+    mat_of = np.array([mat_ids.index(int(s)) for s in d["sub"]], dtype=np.int32)
+    c = S.SolidCase(et, conn, xyz, mats=mats, mat_of=mat_of, penalty=float(kv.get("BCs/displacement_penalty", 1.0e5)))
+    key2side = {}
+    for s, loc in enumerate(S.SIDE_NODES[et]):
+        for e, key in enumerate(map(tuple, np.sort(conn[:, list(loc)], axis=1))):
+            key2side.setdefault(key, (e, s))
+    ns = 3 if et == TET4 else 4
+    for bc in sorted(int(v) for v in kv.get("BCs", "0").split()):
+        disp = [float(kv.get(f"BC/{bc}/displacement/{k}", 0.0)) for k in range(3)]
+        faces = [key2side[tuple(sorted(int(v) for v in n[:ns]))] for t, n in zip(d["face_tag"], d["face_nodes"]) if t == bc]
+        c.add_bc(bc, disp, faces)
+    g = lambda k, dflt: float(kv.get(k, dflt))
+    c.opts.update(max_nonlinear_iterations=int(g("solver/nonlinear/max_nonlinear_iterations", 100)),
+                  relative_step_tolerance=g("solver/nonlinear/relative_step_tolerance", 1e-3),
+                  relative_residual_tolerance=g("solver/nonlinear/relative_residual_tolerance", 1e-8),
+                  absolute_residual_tolerance=g("solver/nonlinear/absolute_residual_tolerance", 1e-8),
+                  require_reduction=kv.get("solver/nonlinear/require_reduction", "false") == "true",
+                  max_linear_iterations=int(g("solver/linear/max_linear_iterations", 50000)),
+                  initial_linear_tolerance=g("solver/linear/initial_linear_tolerance", 1e-3))
+    if tight:
+        c.opts.update(max_nonlinear_iterations=25, relative_step_tolerance=1e-11, relative_residual_tolerance=1e-13,
+                      absolute_residual_tolerance=1e-11 * c.penalty * 1e-6, initial_linear_tolerance=1e-10)
+    return c, kv, d

@@ -378,3 +378,54 @@ def test_cpp_driver_coupled_hcc_with_solid(tmp_path):
                            "solution_out=" + sol], capture_output=True, text=True, timeout=300)
     assert out2.returncode == 0, out2.stdout + out2.stderr
     assert np.linalg.norm(np.fromfile(sol) - u_drv) > 3e-8 * np.linalg.norm(u_drv)
+
+
+@pytest.mark.parametrize("name", ["solid_uniaxial", "solid_hydrogel"])
+def test_cpp_driver_on_the_shipped_solid_cases(tmp_path, name):
+    """The two solid-mechanics run directories the reference ships (run/Solid/uniaxial_compression: 512 HEX8, the cube pressed
+    to half its height in 10 load steps; run/Solid/hydrogel_tension: 5504 TET4, symmetry planes + a pulled face), rebuilt
+    verbatim from tests/golden/solid_*.npz (mesh with its tagged faces, the input.dat text) and run by `rdc_driver -m solid`.
+    (a) as shipped: relative step tolerance 1e-3 and linear tolerance 1e-3 -- two correct drivers agree to those tolerances;
+    (b) the same files with the solver tolerances tightened: positions equal to the oracle's to 1e-8."""
+    import re
+    import solid_cases as SC
+    from oracle import solid as S
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "driver"), "-s"])
+    c, kv, fx = SC.shipped_case(name)
+    d = str(tmp_path)
+    faces = [(int(t), [int(v) for v in n if v >= 0]) for t, n in zip(fx["face_tag"], fx["face_nodes"])]
+    _write_gmsh_with_faces(os.path.join(d, str(fx["mesh_name"])), c.conn, c.xund, fx["sub"], faces)
+    text = str(fx["input_dat"])
+    nload = int(1.0 / float(kv["loading_step"]))
+
+    def run(input_text, steps):
+        with open(os.path.join(d, "input.dat"), "w") as f:
+            f.write(input_text)
+        sol = os.path.join(d, "x.bin")
+        out = subprocess.run([os.path.join(ROOT, "driver", "rdc_driver"), "-m", "solid", os.path.join(d, "input.dat"), "ksp=0",
+                              "vtu=binary", "solution_out=" + sol], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert out.stdout.count("Newton iterations") == steps and "NOT converged" not in out.stdout
+        return np.fromfile(sol)[:3 * c.N]
+
+    # (a) verbatim
+    x_drv = run(text, nload)
+    orc = S.OracleSolid(c)
+    x = c.xund.copy().ravel()
+    for l in range(1, nload + 1):
+        x, info = orc.newton(x, float(kv["loading_step"]) * l)
+        assert info["converged"]
+    disp = np.abs(x - c.xund.ravel()).max()
+    assert np.abs(x_drv - x).max() <= 5e-3 * disp, (np.abs(x_drv - x).max(), disp)
+    assert os.path.exists(os.path.join(d, "out-%d.vtu" % nload))        # output_PARAVIEW = out, last load step
+    # (b) tightened, three load steps
+    tight = re.sub(r"(?m)^loading_step.*$", "loading_step = 0.34", text) + _TIGHT + "solver/nonlinear/absolute_residual_tolerance = 1e-14\n"
+    x_drv = run(tight, 2)
+    ct, _, _ = SC.shipped_case(name, tight=True)
+    ct.opts.update(absolute_residual_tolerance=1e-14)
+    orc = S.OracleSolid(ct)
+    x = ct.xund.copy().ravel()
+    for l in (1, 2):
+        x, info = orc.newton(x, 0.34 * l)
+        assert info["converged"]
+    assert np.linalg.norm(x_drv - x) <= 1e-8 * np.linalg.norm(x)

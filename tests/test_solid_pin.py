@@ -114,3 +114,22 @@ def test_newton_load_steps_converge(et):
     bot = np.abs(c.xund[:, 2]) < 1e-9
     assert np.abs(X[top, 2] - (1.5 - 0.75 * 0.2 * 1.000001)).max() < 1e-4      # ratio = pseudo_time * 1.000001 (solid_system.C:285)
     assert np.abs(X[bot] - c.xund[bot]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["solid_uniaxial", "solid_hydrogel"])
+def test_shipped_solid_cases_match_reference(name):
+    """run/Solid/uniaxial_compression (cube.msh, HEX8) and run/Solid/hydrogel_tension (hydrogel_model.msh, TET4) as shipped:
+    mesh, tagged boundary faces, BC table and penalty of the input.dat; Jacobian, residual and post-processing of a state
+    away from equilibrium -- oracle against the reference's own sources."""
+    c, kv, d = SC.shipped_case(name)
+    h = float(np.linalg.norm(c.xund.max(axis=0) - c.xund.min(axis=0)))
+    x = c.xund + 2e-3 * h * np.random.default_rng(4).normal(size=c.xund.shape)
+    orc, ref = S.OracleSolid(c), S.RefSolid(c)
+    val, rhs = orc.assemble(x, 0.4)
+    rp, cl, vr, rr = ref.assemble(x, 0.4)
+    assert np.array_equal(rp, orc.rowptr) and np.array_equal(cl, orc.col)
+    assert np.abs(val - vr).max() <= 1e-12 * np.abs(vr).max()
+    assert np.abs(rhs - rr).max() <= 1e-12 * np.abs(rr).max()
+    po, vo, fo = orc.post(x, 0.4)
+    pr, vr2, fr = ref.post(x, 0.4)
+    assert np.array_equal(po, pr) and np.array_equal(vo, vr2) and np.array_equal(fo, fr)
