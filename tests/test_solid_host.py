@@ -63,3 +63,37 @@ def test_post_process_matches_oracle(et):
         out = G.probe_post(et, x[nodes], c.xund[nodes], c.mats[c.mat_of[e]], 0.4, c.fibres[e])
         assert abs(out[0] - po[e]) <= 1e-12 * scale and abs(out[1] - vo[e]) <= 1e-12 * scale
         assert np.abs(out[2:] - fo[e]).max() <= 1e-13
+
+
+def test_tangent_rows_on_random_elements():
+    """Random affine-plus-noise elements, deformation gradients, materials (Young 1e1..1e5, Poisson 0..0.45, with and without
+    fibres) and anisotropic growth: the closed form equals the oracle's literal 3^8 evaluation to 1e-13 of the largest entry."""
+    import ctypes as C
+    from oracle import oracle as O
+    L = O.lib()
+    L.orc_solid_element.restype = C.c_int
+    rng = np.random.default_rng(0)
+    base = {SC.TET4: np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float),
+            SC.HEX8: np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], float)}
+    done = 0
+    for trial in range(120):
+        et = SC.TET4 if trial % 2 == 0 else SC.HEX8
+        A = np.eye(3) + 0.3 * rng.normal(size=(3, 3))
+        Fd = np.eye(3) + 0.25 * rng.normal(size=(3, 3))
+        if np.linalg.det(A) < 0.2 or np.linalg.det(Fd) < 0.3:
+            continue
+        Xu = np.ascontiguousarray(base[et] @ A.T * rng.uniform(0.01, 10) + 0.05 * rng.normal(size=base[et].shape))
+        Xc = np.ascontiguousarray(Xu @ Fd.T + 0.02 * rng.normal(size=Xu.shape) * np.abs(Xu).max())
+        mat = np.array([10 ** rng.uniform(1, 5), rng.uniform(0.0, 0.45), rng.choice([0.0, 10 ** rng.uniform(0, 3)]), *rng.uniform(-0.5, 0.8, 3)])
+        t, eta = rng.uniform(0, 1), rng.normal(size=3)
+        Re, Ke = np.zeros(3 * et), np.zeros((3 * et, 3 * et))
+        assert L.orc_solid_element(C.c_int(et), S._p(Xc), S._p(Xu), S._p(mat), C.c_double(t), S._p(eta), C.c_int(1), C.c_int(0), S._p(Re), S._p(Ke)) == 0
+        if not np.isfinite(Ke).all():
+            continue
+        K4, R2 = Ke.reshape(3, et, 3, et), Re.reshape(3, et)
+        for li in range(et):
+            R, K = G.probe_row(et, Xc, Xu, mat, t, eta, li)
+            assert np.abs(R - R2[:, li]).max() <= 1e-13 * np.abs(Re).max()
+            assert np.abs(K - K4[:, li]).max() <= 1e-13 * np.abs(Ke).max()
+        done += 1
+    assert done >= 60
