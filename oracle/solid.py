@@ -99,7 +99,7 @@ class OracleSolid:
             getattr(self.L, n).restype = C.c_int
         self.L.orc_eig3.restype = None
         nen = 4 if case.elem_type == TET4 else 8
-        self.rowptr, self.col = O.build_pattern(case.N, case.conn, 3) if hasattr(O, "build_pattern") else self._pattern(nen)
+        self.rowptr, self.col = self._pattern(nen)   # (node graph + I) x dense 3x3, what libMesh preallocates
 
     def _pattern(self, nen):
         c = self.c
