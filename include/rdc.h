@@ -265,6 +265,11 @@ int rdc_solid_probe_bc_row(int ns, const double* x_cur, const double* x_und, con
                            int i, double* R, double* Kd);
 int rdc_solid_probe_post(int elem_type, const double* x_cur, const double* x_und, const double* mat6, double pseudo_time,
                          const double* eta, double* out5);
+/* host-only probe of the penalty-row lists of rank `rank` of an nranks job (CPU world-size-2 tests): rows as global node ids,
+ * entries (side index into the input, position of the node inside that side) in the order the terms are added; rdc_free */
+int rdc_solid_probe_bc_rows(int elem_type, int64_t n_nodes, int64_t n_elems, const int32_t* conn, const double* xyz, int rank,
+                            int nranks, int partitioner, int64_t nside, const int64_t* side_elem, const int32_t* side_no,
+                            int32_t* n_rows, int32_t** row_node_glob, int32_t** row_ptr, int32_t** ent_side, int32_t** ent_pos);
 
 /* read-only streaming probe over the stored operator values (reference point for the SpMV roofline): mean ms, bytes */
 int rdc_bench_stream(rdc_ctx*, int reps, int ctas_per_sm, double* mean_ms, int64_t* bytes);

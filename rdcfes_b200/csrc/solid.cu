@@ -333,6 +333,49 @@ extern "C" int rdc_solid_set_fibres(rdc_ctx* c, const double* fibres) {
   return put(c, &W->d_fibres, loc);
 }
 
+// Host-only: which owned rows carry penalty terms and in which order.  conn = LOCAL connectivity (local node ids, owned nodes
+// first), loc_of = global element -> local element or -1.  A side whose element is not local is skipped (every element that
+// touches an owned node is local, so an owned boundary node sees all of its sides); an owned node's entries keep the input
+// order of the sides -- the order the penalty terms are added in (fixed => bit-reproducible).
+namespace rdc {
+struct SolidBcLists {
+  std::vector<int32_t> row_node, row_ptr, ent_side, ent_pos, side_node, side_bc;
+};
+int solid_build_bc_lists(int nen, int32_t n_owned, const std::vector<int32_t>& conn, const std::vector<int64_t>& loc_of, int nbc, int64_t nside,
+                         const int64_t* side_elem, const int32_t* side_no, const int32_t* side_bc, SolidBcLists& L, std::string& err) {
+  static const int tet[4][4] = {{0, 2, 1, -1}, {0, 1, 3, -1}, {1, 2, 3, -1}, {2, 0, 3, -1}};     // [upstream] side_nodes_map
+  static const int hex[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+  const int ns = nen == 4 ? 3 : 4, nsides = nen == 4 ? 4 : 6;
+  const int64_t E_glob = (int64_t)loc_of.size();
+  L.side_node.assign((size_t)nside * 4, -1);
+  L.side_bc.assign((size_t)nside, 0);
+  std::vector<std::vector<std::pair<int32_t, int32_t>>> per_node((size_t)n_owned);   // owned node -> (side, position), input order
+  for (int64_t k = 0; k < nside; k++) {
+    if (side_elem[k] < 0 || side_elem[k] >= E_glob || side_no[k] < 0 || side_no[k] >= nsides || side_bc[k] < 0 || side_bc[k] >= nbc) {
+      err = "rdc_solid_set_bcs: side out of range";
+      return RDC_E_ARG;
+    }
+    const int64_t le = loc_of[side_elem[k]];
+    L.side_bc[k] = side_bc[k];
+    if (le < 0) continue;   // not on this rank
+    for (int j = 0; j < ns; j++) {
+      const int32_t nd = conn[(size_t)le * nen + (nen == 4 ? tet[side_no[k]][j] : hex[side_no[k]][j])];
+      L.side_node[(size_t)k * 4 + j] = nd;
+      if (nd < n_owned) per_node[nd].push_back({(int32_t)k, (int32_t)j});
+    }
+  }
+  L.row_node.clear(); L.ent_side.clear(); L.ent_pos.clear();
+  L.row_ptr.assign(1, 0);
+  for (int32_t nd = 0; nd < n_owned; nd++) {
+    if (per_node[nd].empty()) continue;
+    L.row_node.push_back(nd);
+    for (auto& sp : per_node[nd]) { L.ent_side.push_back(sp.first); L.ent_pos.push_back(sp.second); }
+    L.row_ptr.push_back((int32_t)L.ent_side.size());
+  }
+  return 0;
+}
+}  // namespace rdc
+
 // Boundary sides with their conditions: side k = side `side_no[k]` (libMesh side order) of element `side_elem[k]` carries
 // boundary condition `side_bc[k]`, whose prescribed displacement is bc_disp[3*side_bc[k] ..] (NaN = component free);
 // es.parameters "BCs", "BC/<id>/displacement", "BCs/displacement_penalty" + BoundaryInfo (solid_system.C:288-304).
@@ -344,43 +387,51 @@ extern "C" int rdc_solid_set_bcs(rdc_ctx* c, int nbc, const double* bc_disp, int
   int rc = solid_work(c, &W);
   if (rc) return rc;
   const HostSetup& S = c->S;
-  static const int tet[4][4] = {{0, 2, 1, -1}, {0, 1, 3, -1}, {1, 2, 3, -1}, {2, 0, 3, -1}};     // [upstream] side_nodes_map
-  static const int hex[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
-  const int nen = c->nen, ns = nen == 4 ? 3 : 4, nsides = nen == 4 ? 4 : 6;
+  const int nen = c->nen, ns = nen == 4 ? 3 : 4;
   // local connectivity back from the device (the host copy is dropped after rdc_create)
   std::vector<int32_t> conn((size_t)S.E_loc * nen);
   RDC_CUDA(cudaMemcpy(conn.data(), c->d_conn, conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
   std::vector<int64_t> loc_of(S.E_glob, -1);
   for (int64_t le = 0; le < S.E_loc; le++) loc_of[S.elem_glob[le]] = le;
-  std::vector<int32_t> side_node((size_t)nside * 4, -1), sbc((size_t)nside);
-  std::vector<std::vector<std::pair<int32_t, int32_t>>> per_node(S.n_owned);   // owned node -> (side, position), input order
-  for (int64_t k = 0; k < nside; k++) {
-    if (side_elem[k] < 0 || side_elem[k] >= S.E_glob || side_no[k] < 0 || side_no[k] >= nsides || side_bc[k] < 0 || side_bc[k] >= nbc) {
-      c->err = "rdc_solid_set_bcs: side out of range";
-      return RDC_E_ARG;
-    }
-    const int64_t le = loc_of[side_elem[k]];
-    sbc[k] = side_bc[k];
-    if (le < 0) continue;   // not on this rank
-    for (int j = 0; j < ns; j++) {
-      const int32_t nd = conn[(size_t)le * nen + (nen == 4 ? tet[side_no[k]][j] : hex[side_no[k]][j])];
-      side_node[(size_t)k * 4 + j] = nd;
-      if (nd < S.n_owned) per_node[nd].push_back({(int32_t)k, (int32_t)j});
-    }
-  }
-  std::vector<int32_t> row_node, row_ptr(1, 0), ent_side, ent_pos;
-  for (int32_t nd = 0; nd < S.n_owned; nd++) {
-    if (per_node[nd].empty()) continue;
-    row_node.push_back(nd);
-    for (auto& sp : per_node[nd]) { ent_side.push_back(sp.first); ent_pos.push_back(sp.second); }
-    row_ptr.push_back((int32_t)ent_side.size());
-  }
+  SolidBcLists L;
+  if ((rc = solid_build_bc_lists(nen, S.n_owned, conn, loc_of, nbc, nside, side_elem, side_no, side_bc, L, c->err))) return rc;
   std::vector<double> disp(bc_disp, bc_disp + (size_t)nbc * 3);
-  if ((rc = put(c, &W->d_row_node, row_node)) || (rc = put(c, &W->d_row_ptr, row_ptr)) || (rc = put(c, &W->d_ent_side, ent_side)) ||
-      (rc = put(c, &W->d_ent_pos, ent_pos)) || (rc = put(c, &W->d_side_node, side_node)) || (rc = put(c, &W->d_side_bc, sbc)) ||
+  if ((rc = put(c, &W->d_row_node, L.row_node)) || (rc = put(c, &W->d_row_ptr, L.row_ptr)) || (rc = put(c, &W->d_ent_side, L.ent_side)) ||
+      (rc = put(c, &W->d_ent_pos, L.ent_pos)) || (rc = put(c, &W->d_side_node, L.side_node)) || (rc = put(c, &W->d_side_bc, L.side_bc)) ||
       (rc = put(c, &W->d_bc_disp, disp)))
     return rc;
-  W->nrow = (int)row_node.size(); W->nside = (int)nside; W->ns = ns; W->penalty = penalty;
+  W->nrow = (int)L.row_node.size(); W->nside = (int)nside; W->ns = ns; W->penalty = penalty;
+  return RDC_OK;
+}
+
+// Host-only probe of the penalty-row lists of rank `rank` of an `nranks` job (no device needed; the CPU world-size-2 tests use
+// it): rows as GLOBAL node ids, entries as (side index into the input, position of the row's node inside that side).  Arrays
+// are malloc'ed by the library (rdc_free).
+extern "C" int rdc_solid_probe_bc_rows(int elem_type, int64_t n_nodes, int64_t n_elems, const int32_t* conn, const double* xyz, int rank,
+                                       int nranks, int partitioner, int64_t nside, const int64_t* side_elem, const int32_t* side_no,
+                                       int32_t* n_rows, int32_t** row_node_glob, int32_t** row_ptr, int32_t** ent_side, int32_t** ent_pos) {
+  if ((elem_type != RDC_TET4 && elem_type != RDC_HEX8) || !conn || !xyz || !n_rows || !row_node_glob || !row_ptr || !ent_side || !ent_pos)
+    return RDC_E_ARG;
+  HostSetup S;
+  std::string err;
+  int rc;
+  try {
+    rc = build_setup(S, elem_type, 3, n_nodes, n_elems, conn, xyz, rank, nranks, partitioner, 128, 1, err);
+  } catch (const std::bad_alloc&) { rc = RDC_E_NOMEM; }
+  if (rc) return rc;
+  std::vector<int64_t> loc_of((size_t)n_elems, -1);
+  for (int64_t le = 0; le < S.E_loc; le++) loc_of[S.elem_glob[le]] = le;
+  std::vector<int32_t> bc((size_t)std::max<int64_t>(nside, 1), 0);
+  SolidBcLists L;
+  if ((rc = solid_build_bc_lists(S.nen, S.n_owned, S.conn, loc_of, 1, nside, side_elem, side_no, bc.data(), L, err))) return rc;
+  for (auto& nd : L.row_node) nd = S.loc2glob[nd];
+  auto dup = [](const std::vector<int32_t>& v) {
+    int32_t* p = (int32_t*)malloc(sizeof(int32_t) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) memcpy(p, v.data(), sizeof(int32_t) * v.size());
+    return p;
+  };
+  *n_rows = (int32_t)L.row_node.size();
+  *row_node_glob = dup(L.row_node); *row_ptr = dup(L.row_ptr); *ent_side = dup(L.ent_side); *ent_pos = dup(L.ent_pos);
   return RDC_OK;
 }
 

@@ -40,7 +40,7 @@ EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_dis
            "rdc_version", "rdc_probe_partition", "rdc_set_option", "rdc_set_subdomains", "rdc_region_volumes",
            "rdc_region_last_mean", "rdc_probe_spmv_tiles", "rdc_probe_region_chunks",
            "rdc_solid_set_reference", "rdc_solid_set_materials", "rdc_solid_set_fibres", "rdc_solid_set_bcs", "rdc_solid_assemble",
-           "rdc_solid_newton", "rdc_solid_post_process", "rdc_solid_probe_row", "rdc_solid_probe_bc_row", "rdc_solid_probe_post"]
+           "rdc_solid_newton", "rdc_solid_post_process", "rdc_solid_probe_row", "rdc_solid_probe_bc_row", "rdc_solid_probe_post", "rdc_solid_probe_bc_rows"]
 
 
 def load():
@@ -93,6 +93,8 @@ def load():
         "rdc_solid_probe_row": [i32, vp, vp, vp, f64, vp, i32, vp, vp],
         "rdc_solid_probe_bc_row": [i32, vp, vp, vp, f64, f64, i32, vp, vp],
         "rdc_solid_probe_post": [i32, vp, vp, vp, f64, vp, vp],
+        "rdc_solid_probe_bc_rows": [i32, i64, i64, vp, vp, i32, i32, i32, i64, vp, vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp),
+                                    C.POINTER(vp), C.POINTER(vp)],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)

@@ -182,3 +182,23 @@ def probe_post(elem_type, Xc, Xu, mat6, pseudo_time, eta):
     rc = L.rdc_solid_probe_post(elem_type, _ptr(Xc), _ptr(Xu), _ptr(m), float(pseudo_time), _ptr(e), _ptr(out))
     assert rc == 0
     return out
+
+
+def probe_bc_rows(elem_type, conn, xyz, rank, nranks, partitioner, side_elem, side_no):
+    """Penalty-row lists of one rank (host only): {global node: [(side index, position in the side), ...]} in adding order."""
+    L = _lib.load()
+    conn = np.ascontiguousarray(conn, dtype=np.int32); xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    se = np.ascontiguousarray(side_elem, dtype=np.int64); sn = np.ascontiguousarray(side_no, dtype=np.int32)
+    n = C.c_int32()
+    rn, rp, es, ep = (C.c_void_p() for _ in range(4))
+    rc = L.rdc_solid_probe_bc_rows(elem_type, xyz.shape[0], conn.shape[0], _ptr(conn), _ptr(xyz), rank, nranks, partitioner, se.shape[0],
+                                   _ptr(se), _ptr(sn), C.byref(n), C.byref(rn), C.byref(rp), C.byref(es), C.byref(ep))
+    assert rc == 0, rc
+    def take(p, count):
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(max(count, 1),))[:count].copy()
+        L.rdc_free(p)
+        return a
+    nr = n.value
+    row_ptr = take(rp, nr + 1)
+    nodes, side, pos = take(rn, nr), take(es, int(row_ptr[-1]) if nr else 0), take(ep, int(row_ptr[-1]) if nr else 0)
+    return {int(nodes[k]): list(zip(side[row_ptr[k]:row_ptr[k + 1]].tolist(), pos[row_ptr[k]:row_ptr[k + 1]].tolist())) for k in range(nr)}

@@ -176,3 +176,55 @@ def test_region_bucketing_invariants():
     for r in range(nreg):                                                        # no chunk straddles two regions
         for c in range(rptr[r], rptr[r + 1]):
             assert np.all(region[perm[cptr[c]:cptr[c + 1]]] == r)
+
+
+# ---- solid mechanics, N > 1: which rank adds which penalty terms (host logic of rdc_solid_set_bcs, probed without a device) --
+def _solid_bc_worker(rank, world, port, partitioner, et, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import solid_cases as SC
+        from oracle import solid as S
+        from rdcfes_b200 import solid as G
+        from rdcfes_b200 import system as rs
+        c = SC.general_case(et, n=5)
+        se, sn, sb, bd = c.arrays()
+        rows = G.probe_bc_rows(et, c.conn, c.xund, rank, world, partitioner, se, sn)
+        owner = rs.probe_partition(et, 3, c.conn, c.xund, rank, world, partitioner)["owner"]
+        # every row belongs to a node this rank owns ...
+        assert all(owner[n] == rank for n in rows)
+        # ... and carries ALL incidences of that node in the boundary sides, in input order: the rank that owns a boundary node adds
+        # every penalty term of its row itself (no cross-rank sum), in the same order on any number of ranks
+        want = {}
+        for k in range(se.shape[0]):
+            for j, l in enumerate(S.SIDE_NODES[et][sn[k]]):
+                want.setdefault(int(c.conn[se[k], l]), []).append((k, j))
+        for n, ent in rows.items():
+            assert ent == want[n], (n, ent, want[n])
+        # the ranks' rows tile the set of boundary-condition nodes: each exactly once
+        cnt = torch.zeros(c.N, dtype=torch.int64)
+        cnt[list(rows)] = 1
+        dist.all_reduce(cnt)
+        expect = torch.zeros(c.N, dtype=torch.int64)
+        expect[list(want)] = 1
+        assert bool((cnt == expect).all())
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        q.put((rank, repr(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,partitioner,et", [(2, 0, 4), (2, 1, 8), (3, 0, 4)])
+def test_solid_penalty_rows_gloo(world, partitioner, et):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_solid_bc_worker, args=(r, world, port, partitioner, et, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
