@@ -240,6 +240,8 @@ class RdcSolidAdapter {
     }
     check(rdc_create(&ctx_, RDC_SOLID, nen, N, (int64_t)E, conn.data(), xund.data(), base.data(), -1), "rdc_create");
     check(rdc_solid_set_reference(ctx_, xund.data()), "rdc_solid_set_reference");
+    check(rdc_solid_set_symmetry(ctx_, es_.parameters.have_parameter<bool>("solver/assembly_use_symmetry") &&
+                                           es_.parameters.get<bool>("solver/assembly_use_symmetry")), "rdc_solid_set_symmetry");
     push_positions();
     // materials: one row per distinct subdomain id, keys of solid.C:276-291 (read per element at solid_system.C:182-189)
     std::vector<int> ids(sub);

@@ -196,9 +196,10 @@ static SolidModel make_solid(const Input& in, const Mesh& mesh, const std::strin
   auto ck = [&](int rc, const char* what) {
     if (rc) die(std::string(what) + ": " + rdc_last_error(sm.ctx));
   };
-  if (in.integer("solver/assembly_use_symmetry", 0) || in.str("solver/assembly_use_symmetry", "false") == "true")
-    die("solver/assembly_use_symmetry = true (mirrored upper triangle, solid_system.C:248-262) is not offered by the device path");
   ck(rdc_create(&sm.ctx, RDC_SOLID, mesh.nen, N, E, mesh.conn.data(), mesh.xyz.data(), nullptr, -1), "rdc_create(solid)");
+  // solid.C:243-244 (the shipped files spell it solver/use_symmetry, which is never read: default false)
+  ck(rdc_solid_set_symmetry(sm.ctx, in.integer("solver/assembly_use_symmetry", 0) || in.str("solver/assembly_use_symmetry", "false") == "true"),
+     "rdc_solid_set_symmetry");
   ck(rdc_set_solution(sm.ctx, mesh.xyz.data()), "rdc_set_solution");            // mesh_position_get (solid_system.C:82)
   ck(rdc_solid_set_reference(sm.ctx, mesh.xyz.data()), "rdc_solid_set_reference");   // save_initial_mesh (solid.C:68)
   // materials = the subdomain ids that carry parameters (solid.C:273-291); every element's subdomain must be one of them

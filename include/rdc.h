@@ -251,6 +251,9 @@ int rdc_region_last_mean(rdc_ctx*, int var, double* mean /* [n_regions] */);
 int rdc_solid_set_reference(rdc_ctx*, const double* xyz_undeformed /* [n_nodes*3] */);
 int rdc_solid_set_materials(rdc_ctx*, int nmat, const double* mats /* [nmat*6] */, const int32_t* mat_of /* [n_elems] or NULL */);
 int rdc_solid_set_fibres(rdc_ctx*, const double* fibres /* [n_elems*3] or NULL */);
+/* es.parameters "solver/assembly_use_symmetry" (solid.C:243-244; solid_system.C:180,248-262): 1 = the blocks j >= i of every
+ * element tangent are evaluated and the others mirrored (K_ji = K_ij^T) like the reference does; default 0 */
+int rdc_solid_set_symmetry(rdc_ctx*, int use_symmetry);
 int rdc_solid_set_bcs(rdc_ctx*, int nbc, const double* bc_disp /* [nbc*3] */, int64_t nside, const int64_t* side_elem,
                       const int32_t* side_no, const int32_t* side_bc, double penalty);
 int rdc_solid_assemble(rdc_ctx*, double pseudo_time);
@@ -260,7 +263,7 @@ int rdc_solid_post_process(rdc_ctx*, double pseudo_time, double* press, double* 
  * residual/tangent R[3], K[9*nen] (plane a*3+c, column node j at (a*3+c)*nen + j); the penalty row of node i of a side with
  * ns nodes R[3], Kd[ns*3]; post_process of one element out[5] = {p, von Mises, fibre[3]} */
 int rdc_solid_probe_row(int elem_type, const double* x_cur, const double* x_und, const double* mat6, double pseudo_time,
-                        const double* eta, int li, double* R, double* K);
+                        const double* eta, int li, int use_symmetry, double* R, double* K);
 int rdc_solid_probe_bc_row(int ns, const double* x_cur, const double* x_und, const double* disp, double pseudo_time, double penalty,
                            int i, double* R, double* Kd);
 int rdc_solid_probe_post(int elem_type, const double* x_cur, const double* x_und, const double* mat6, double pseudo_time,

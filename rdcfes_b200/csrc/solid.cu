@@ -34,6 +34,7 @@ struct SolidArgs {
   const int32_t* mat_of;    // [E_loc] or null
   const double* fibres;     // [E_loc*3] or null
   double pseudo_time;
+  int use_symmetry;         // solver/assembly_use_symmetry (solid_system.C:180)
   double mats[SOLID_MAX_MAT][6];
 };
 
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(PAIRS, 1) k_solid_assemble(const AsmArgs A, co
     double* K = stageK + tid;
 #pragma unroll
     for (int k = 0; k < NKV * NEN; k++) K[(size_t)k * PAIRS] = 0.0;
-    solid_row<NEN>(c_fe_solid[TI], Xc, Xu, mat, S.pseudo_time, eta, li, R, K, PAIRS);
+    solid_row<NEN>(c_fe_solid[TI], Xc, Xu, mat, S.pseudo_time, eta, li, R, K, PAIRS, S.use_symmetry);
 #pragma unroll
     for (int a = 0; a < NV; a++) stageF[a * PAIRS + tid] = R[a];
   }
@@ -225,6 +226,7 @@ struct SolidWork {
   int32_t *d_row_node = nullptr, *d_row_ptr = nullptr, *d_ent_side = nullptr, *d_ent_pos = nullptr, *d_side_node = nullptr, *d_side_bc = nullptr;
   double* d_bc_disp = nullptr;
   double penalty = 1.0e5;
+  int use_symmetry = 0;
   // Newton scratch
   double *d_dx = nullptr, *d_partial = nullptr, *d_post = nullptr;
   bool tables = false;
@@ -314,6 +316,17 @@ extern "C" int rdc_solid_set_materials(rdc_ctx* c, int nmat, const double* mats,
     }
     if ((rc = put(c, &W->d_mat_of, loc))) return rc;
   }
+  return RDC_OK;
+}
+
+// es.parameters "solver/assembly_use_symmetry" (solid.C:243-244, solid_system.C:180,248-262): blocks j >= i evaluated, the rest mirrored
+extern "C" int rdc_solid_set_symmetry(rdc_ctx* c, int use_symmetry) {
+  CHECK_SOLID(c);
+  SolidWork* W;
+  int rc = solid_work(c, &W);
+  if (rc) return rc;
+  W->use_symmetry = use_symmetry != 0;
+  c->assembled = false;
   return RDC_OK;
 }
 
@@ -437,6 +450,7 @@ extern "C" int rdc_solid_probe_bc_rows(int elem_type, int64_t n_nodes, int64_t n
 
 static void fill_solid_args(const SolidWork* W, double pseudo_time, SolidArgs* S) {
   S->xund = W->d_xund; S->mat_of = W->d_mat_of; S->fibres = W->d_fibres; S->pseudo_time = pseudo_time;
+  S->use_symmetry = W->use_symmetry;
   memcpy(S->mats, W->mats, sizeof(S->mats));
 }
 
@@ -662,13 +676,13 @@ static const FeTable& host_table(int elem_type) {
 }
 // row `li` of one element: R[3], K[9*nen] (entry plane a*3+c, column node j at K[(a*3+c)*nen + j])
 extern "C" int rdc_solid_probe_row(int elem_type, const double* Xc, const double* Xu, const double* mat6, double pseudo_time,
-                                   const double* eta, int li, double* R, double* K) {
+                                   const double* eta, int li, int use_symmetry, double* R, double* K) {
   if ((elem_type != RDC_TET4 && elem_type != RDC_HEX8) || !Xc || !Xu || !mat6 || !eta || !R || !K) return RDC_E_ARG;
   const int nen = elem_type == RDC_TET4 ? 4 : 8;
   for (int k = 0; k < 3; k++) R[k] = 0.0;
   for (int k = 0; k < 9 * nen; k++) K[k] = 0.0;
-  if (nen == 4) solid_row<4>(host_table(elem_type), (const double (*)[3])Xc, (const double (*)[3])Xu, mat6, pseudo_time, eta, li, R, K, 1);
-  else solid_row<8>(host_table(elem_type), (const double (*)[3])Xc, (const double (*)[3])Xu, mat6, pseudo_time, eta, li, R, K, 1);
+  if (nen == 4) solid_row<4>(host_table(elem_type), (const double (*)[3])Xc, (const double (*)[3])Xu, mat6, pseudo_time, eta, li, R, K, 1, use_symmetry);
+  else solid_row<8>(host_table(elem_type), (const double (*)[3])Xc, (const double (*)[3])Xu, mat6, pseudo_time, eta, li, R, K, 1, use_symmetry);
   return RDC_OK;
 }
 // penalty row of node `i` of a side with ns nodes: R[3], Kd[ns*3]

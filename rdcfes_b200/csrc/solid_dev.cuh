@@ -122,9 +122,12 @@ RDC_HD void solid_point(const double (*Xu)[3], const double (*dphi)[3], const do
 
 // Row `li` of the element residual and tangent (element term only), accumulated over the quadrature points:
 //   R[a] and K[(a*3 + c) * NEN + j] * kstride  (entry plane a*3+c, column node j); the caller zeroes K and R.
+// use_symmetry = es.parameters "solver/assembly_use_symmetry" (solid_system.C:180,248-262): the reference then evaluates
+// the blocks j >= i only and mirrors them, K_ji = (K_ij)^T; with growth or fibres the exact tangent is not symmetric, so this
+// is a different matrix.  Row li therefore takes its blocks j < li as the transpose of block (j, li).
 template <int NEN>
 RDC_HD void solid_row(const FeTable& T, const double (*Xc)[3], const double (*Xu)[3], const double* mat, double pseudo_time,
-                      const double* eta, int li, double* R, double* K, int kstride) {
+                      const double* eta, int li, double* R, double* K, int kstride, int use_symmetry = 0) {
   // TET4: the map is affine, so grad phi, F and with them sigma and the tangent are the same at all five points of the
   // rule -- one evaluation carries the whole weight sum(w_q) = 1/6 (w_0 = -2/15 times -5/4).  HEX8: per point.
   constexpr int NQP = NEN == 4 ? 1 : 8;
@@ -156,6 +159,26 @@ RDC_HD void solid_row(const FeTable& T, const double (*Xc)[3], const double (*Xu
       for (int a = 0; a < 3; a++) Qh[a] = S.Q[a][0] * h[0] + S.Q[a][1] * h[1] + S.Q[a][2] * h[2];
       const double gQh = g[0] * Qh[0] + g[1] * Qh[1] + g[2] * Qh[2];
       const double geo = JxW * (sg[0] * h[0] + sg[1] * h[1] + sg[2] * h[2]);    // G_NN, hyperelastic.h:83-85
+      if (use_symmetry && j < li) {
+        // mirrored block: K_{li,j}[a][c] = K_{j,li}[c][a], i.e. the formula with the roles of g and h exchanged, transposed
+        double Ph[3], Qg[3], Qth[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          Ph[a] = S.P[a][0] * h[0] + S.P[a][1] * h[1] + S.P[a][2] * h[2];
+          Qg[a] = S.Q[a][0] * g[0] + S.Q[a][1] * g[1] + S.Q[a][2] * g[2];
+          Qth[a] = S.Q[0][a] * h[0] + S.Q[1][a] * h[1] + S.Q[2][a] * h[2];
+        }
+        const double hQg = h[0] * Qg[0] + h[1] * Qg[1] + h[2] * Qg[2];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            double v = wa * Ph[c] * g[a] - wb * (S.Q[c][a] * hQg + Qg[c] * Qth[a]);
+            if (a == c) v += geo;
+            K[(size_t)((a * 3 + c) * NEN + j) * kstride] += v;
+          }
+        continue;
+      }
 #pragma unroll
       for (int a = 0; a < 3; a++)
 #pragma unroll

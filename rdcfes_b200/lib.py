@@ -39,7 +39,7 @@ EXPORTS = ["rdc_model_nvars", "rdc_model_nparams", "rdc_create", "rdc_create_dis
            "rdc_spmv", "rdc_bench_spmv", "rdc_bench_stream", "rdc_bench_barrier", "rdc_bench_dfma", "rdc_download_csr", "rdc_free", "rdc_get_stats", "rdc_set_stream",
            "rdc_version", "rdc_probe_partition", "rdc_set_option", "rdc_set_subdomains", "rdc_region_volumes",
            "rdc_region_last_mean", "rdc_probe_spmv_tiles", "rdc_probe_region_chunks",
-           "rdc_solid_set_reference", "rdc_solid_set_materials", "rdc_solid_set_fibres", "rdc_solid_set_bcs", "rdc_solid_assemble",
+           "rdc_solid_set_reference", "rdc_solid_set_materials", "rdc_solid_set_fibres", "rdc_solid_set_symmetry", "rdc_solid_set_bcs", "rdc_solid_assemble",
            "rdc_solid_newton", "rdc_solid_post_process", "rdc_solid_probe_row", "rdc_solid_probe_bc_row", "rdc_solid_probe_post", "rdc_solid_probe_bc_rows"]
 
 
@@ -87,10 +87,10 @@ def load():
                              C.POINTER(vp), C.POINTER(vp)],
         "rdc_get_stats": [vp, C.POINTER(Stats)], "rdc_set_stream": [vp, vp], "rdc_set_option": [vp, C.c_char_p, i32], "rdc_set_subdomains": [vp, vp, i32],
         "rdc_region_volumes": [vp, i32, vp, vp], "rdc_region_last_mean": [vp, i32, vp],
-        "rdc_solid_set_reference": [vp, vp], "rdc_solid_set_materials": [vp, i32, vp, vp], "rdc_solid_set_fibres": [vp, vp],
+        "rdc_solid_set_reference": [vp, vp], "rdc_solid_set_materials": [vp, i32, vp, vp], "rdc_solid_set_fibres": [vp, vp], "rdc_solid_set_symmetry": [vp, i32],
         "rdc_solid_set_bcs": [vp, i32, vp, i64, vp, vp, vp, f64], "rdc_solid_assemble": [vp, f64],
         "rdc_solid_newton": [vp, f64, vp, i32, vp], "rdc_solid_post_process": [vp, f64, vp, vp, vp],
-        "rdc_solid_probe_row": [i32, vp, vp, vp, f64, vp, i32, vp, vp],
+        "rdc_solid_probe_row": [i32, vp, vp, vp, f64, vp, i32, i32, vp, vp],
         "rdc_solid_probe_bc_row": [i32, vp, vp, vp, f64, f64, i32, vp, vp],
         "rdc_solid_probe_post": [i32, vp, vp, vp, f64, vp, vp],
         "rdc_solid_probe_bc_rows": [i32, i64, i64, vp, vp, i32, i32, i32, i64, vp, vp, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp),

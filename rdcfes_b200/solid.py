@@ -87,6 +87,9 @@ class SolidSystem:
         f = None if fibres is None else np.ascontiguousarray(fibres, dtype=np.float64).reshape(-1)
         self._check(self._L.rdc_solid_set_fibres(self._h, _ptr(f)))
 
+    def set_symmetry(self, use_symmetry):
+        self._check(self._L.rdc_solid_set_symmetry(self._h, int(bool(use_symmetry))))
+
     def set_bcs(self, bc_disp, side_elem, side_no, side_bc, penalty):
         bd = np.ascontiguousarray(bc_disp, dtype=np.float64).reshape(-1, 3)
         se = np.ascontiguousarray(side_elem, dtype=np.int64)
@@ -146,6 +149,7 @@ def from_case(case, device: int = -1, **dist) -> "SolidSystem":
     s = SolidSystem(case.elem_type, case.conn, case.xund, device=device, **dist)
     s.set_materials(case.mats, case.mat_of)
     s.set_fibres(case.fibres)
+    s.set_symmetry(getattr(case, "use_symmetry", False))
     se, sn, sb, bd = case.arrays()
     s.set_bcs(bd, se, sn, sb, case.penalty)
     s.options.update(case.opts)
@@ -153,13 +157,13 @@ def from_case(case, device: int = -1, **dist) -> "SolidSystem":
 
 
 # ---- host-only probes (no GPU): the same element arithmetic the kernels run, compiled for the host -------------------
-def probe_row(elem_type, Xc, Xu, mat6, pseudo_time, eta, li):
+def probe_row(elem_type, Xc, Xu, mat6, pseudo_time, eta, li, use_symmetry=False):
     L = _lib.load()
     nen = 4 if elem_type == TET4 else 8
     Xc = np.ascontiguousarray(Xc, dtype=np.float64); Xu = np.ascontiguousarray(Xu, dtype=np.float64)
     m = np.ascontiguousarray(mat6, dtype=np.float64); e = np.ascontiguousarray(eta, dtype=np.float64)
     R, K = np.zeros(3), np.zeros(9 * nen)
-    rc = L.rdc_solid_probe_row(elem_type, _ptr(Xc), _ptr(Xu), _ptr(m), float(pseudo_time), _ptr(e), int(li), _ptr(R), _ptr(K))
+    rc = L.rdc_solid_probe_row(elem_type, _ptr(Xc), _ptr(Xu), _ptr(m), float(pseudo_time), _ptr(e), int(li), int(bool(use_symmetry)), _ptr(R), _ptr(K))
     assert rc == 0
     return R, K.reshape(3, 3, nen)
 

@@ -9,9 +9,11 @@ from oracle import solid as S
 from rdcfes_b200 import solid as G
 
 
+@pytest.mark.parametrize("sym", [False, True])
 @pytest.mark.parametrize("et", [SC.TET4, SC.HEX8])
-def test_tangent_rows_match_oracle(et):
-    c = SC.general_case(et, penalty=0.0)
+def test_tangent_rows_match_oracle(et, sym):
+    # sym: solver/assembly_use_symmetry -- blocks j >= i evaluated, the others mirrored (solid_system.C:248-262)
+    c = SC.general_case(et, penalty=0.0, use_symmetry=sym)
     x = SC.perturbed(c)
     orc = S.OracleSolid(c)
     nen = c.conn.shape[1]
@@ -21,7 +23,7 @@ def test_tangent_rows_match_oracle(et):
         Ko = Ko.reshape(3, nen, 3, nen)                     # variable-major: (a, i, c, j)
         nodes = c.conn[e]
         for li in range(nen):
-            R, K = G.probe_row(et, x[nodes], c.xund[nodes], c.mats[c.mat_of[e]], 0.3, c.fibres[e], li)
+            R, K = G.probe_row(et, x[nodes], c.xund[nodes], c.mats[c.mat_of[e]], 0.3, c.fibres[e], li, use_symmetry=sym)
             worst_r = max(worst_r, np.abs(R - Ro.reshape(3, nen)[:, li]).max() / np.abs(Ro).max())
             worst_k = max(worst_k, np.abs(K - Ko[:, li, :, :]).max() / np.abs(Ko).max())
     assert worst_r <= 1e-12 and worst_k <= 1e-12, (worst_r, worst_k)
